@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline benchmark on B200.
+
+Workload (BASELINE.json configs[1], the README example of the reference):
+    mwd_kernel --nx 512 --ny 512 --nz 512 --nt 500 --target-kernel 1 --target-ts 2   (fp64 build)
+i.e. the 7-point constant-coefficient star stencil, fp64, 512^3, 500 time steps, Diamond (MWD)
+stepper.  GIRIH rounds nt to 514 for its default-sized diamonds (t_dim 7) and executes nt-1 = 513
+steps (src/kernels/diamond_utils.c:1042-1056).  One bench "step" = one such stepper
+invocation on data already resident in HBM.  Metric: GLUP/s = interior points x steps executed / s.
+With --gpus N every GPU owns one 512^3 z-slab of a 512 x 512 x (512 N) domain (weak scaling) and
+the slabs exchange T*r-deep halos over NCCL/NVLink.
+
+One JSON line is printed by rank 0 (see the driver contract):
+  value      device-timed, inputs resident (cudaEvents inside the C ABI, max over ranks)
+  e2e        same metric through the C-ABI call sequence with HOST buffers: pinned H2D of U1/U2,
+             stepper, D2H of U1, all inside the timed region
+  roofline   dominant kernel (the fused sweep): algorithmic bytes per launch / measured launch time
+  cpu_baseline  the reference's own OpenMP MWD path on this box's host cores, bounded sample
+
+--impl reference times the reference's CPU implementation (oracle/_ref, built from the unmodified
+sources by oracle/Makefile) on the same workload definition.
+"""
+import argparse
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+KERNEL, NX, NY, NZ, NT, T_DIM = 1, 512, 512, 512, 500, 7
+DTYPE = np.float64
+WORKLOAD = "7pt-const-fp64-512^3-nt500-diamond"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:   # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:   # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:   # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's OpenMP MWD on the host cores
+# ------------------------------------------------------------------------------------------------
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:   # noqa: BLE001
+        return os.cpu_count() or 1
+
+
+def cpu_has_avx512():
+    try:
+        return "avx512f" in open("/proc/cpuinfo").read()
+    except Exception:   # noqa: BLE001
+        return False
+
+
+def reference_mwd_flags(threads, ny):
+    """pinned MWD parameters (the reference's auto-tuner does not finish in minutes):
+    1WD when the thread count allows one diamond per thread, else thread groups along z."""
+    t_dim = T_DIM
+    conc = ny // ((t_dim + 1) * 2)          # diamonds per row (diamond_utils.c:900-901)
+    tgs = 1
+    while threads // tgs > max(1, conc - 1):
+        tgs *= 2
+    threads = max(tgs, threads // tgs * tgs)
+    fl = ["--target-kernel", KERNEL, "--target-ts", 2, "--mwd-type", 2, "--t-dim", t_dim,
+          "--thread-group-size", tgs, "--num-wavefronts", max(4, tgs)]
+    if tgs > 1:
+        fl += ["--thz", tgs, "--thx", 1, "--thy", 1]
+    return threads, fl
+
+
+def run_reference_sample(nz_sample, nt_sample, n_tests=1):
+    """runs oracle/_ref/mwd_kernel_dp_fast* on nx=ny=512, nz=nz_sample; returns dict"""
+    from oracle import girih_oracle as O
+    ref_dir = O.REF_DIR
+    exe = None
+    for cand in (["mwd_kernel_dp_fast512"] if cpu_has_avx512() else []) + ["mwd_kernel_dp_fast", "mwd_kernel_dp"]:
+        if os.path.exists(os.path.join(ref_dir, cand)):
+            exe = os.path.join(ref_dir, cand)
+            break
+    threads = host_threads()
+    if exe is None:
+        # no reference binary travelled: time the oracle port (single-step sweeps, OpenMP over z)
+        pb = O.make_problem(KERNEL, (NX, NY, nz_sample), DTYPE)
+        t0 = time.perf_counter()
+        O.run_steps(pb, nt_sample)
+        dt = time.perf_counter() - t0
+        lups = NX * NY * nz_sample * nt_sample
+        return {"glups": lups / dt / 1e9, "kind": "port", "cores": threads, "seconds": dt,
+                "sample": f"oracle port, {NX}x{NY}x{nz_sample} x {nt_sample} steps"}
+    threads, fl = reference_mwd_flags(threads, NY)
+    cmd = [exe, "--nx", NX, "--ny", NY, "--nz", nz_sample, "--nt", nt_sample, "--n-tests", n_tests,
+           "--verbose", 0] + fl
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="true", OMP_PLACES="cores")
+    t0 = time.perf_counter()
+    out = subprocess.run([str(c) for c in cmd], env=env, capture_output=True, text=True, timeout=1500)
+    dt = time.perf_counter() - t0
+    m = re.search(r"Total RANK0 MStencil/s MAX:\s*([0-9.eE+-]+)", out.stdout)
+    if not m:
+        raise RuntimeError("reference run failed: " + out.stdout[-400:] + out.stderr[-400:])
+    return {"glups": float(m.group(1)) / 1e3, "kind": "reference", "cores": threads, "seconds": dt,
+            "sample": f"{os.path.basename(exe)} {NX}x{NY}x{nz_sample}, nt {nt_sample} (diamond-rounded), "
+                      f"MWD pinned: {' '.join(str(x) for x in fl)}"}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, secs, last = [], [], None
+    for i in range(args.warmup + args.steps):
+        last = run_reference_sample(args.ref_nz, args.ref_nt)
+        if i >= args.warmup:
+            vals.append(last["glups"]); secs.append(last["seconds"])
+    v = statistics.mean(vals)
+    line = {"impl": "reference", "metric": "GLUP/s", "value": v, "unit": "GLUP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(secs),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": last["sample"]},
+            "cpu_baseline": {"value": v, "unit": "GLUP/s", "cores": last["cores"], "kind": last["kind"],
+                             "sample": last["sample"]},
+            "e2e": {"value": v, "unit": "GLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import girih_b200 as G
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    gst = (NX, NY, NZ * world)
+    pb = G.make_problem(KERNEL, gst, DTYPE, rank=rank, nranks=world, pinned=True)
+    s = G.GpuStepper(KERNEL, pb.stencil, pb.shape, DTYPE, device=local, rank=rank, nranks=world)
+    if world > 1:
+        obj = [G.GpuStepper.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        s.comm_init(obj[0])
+    s.upload(pb)
+    if args.tfuse:
+        tf = args.tfuse
+    else:
+        tf = 0
+    nt_eff = G.diamond_nt(NT, T_DIM)
+    nsteps = nt_eff - 1
+    lups_per_step = float(gst[0]) * gst[1] * gst[2] * nsteps
+
+    # ---- device-resident timing ----
+    for _ in range(args.warmup):
+        s.run_fused(nsteps, tf)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    dev_ms, launches = 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s.run_fused(nsteps, tf)
+        dev_ms += s.elapsed_ms()["total"]
+        launches += s.launch_info()["kernels"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_s = allmax(dev_ms * 1e-3)
+    info = s.launch_info()
+    value = lups_per_step * args.steps / dev_s / 1e9
+
+    # ---- end to end: pinned H2D of the fields + stepper + D2H of U1, every step ----
+    h2d = pb.U1.nbytes + pb.U2.nbytes
+    d2h = pb.U1.nbytes
+    out_u1 = torch.empty(pb.U1.shape, dtype=torch.float64).pin_memory().numpy()
+    e2e_steps = max(1, min(args.steps, 3))
+    s.upload_fields(pb.U1, pb.U2); s.run_fused(nsteps, tf); s.download(out_u1, None)   # warm
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        s.upload_fields(pb.U1, pb.U2)
+        s.run_fused(nsteps, tf)
+        s.download(out_u1, None)
+    barrier()
+    e2e_s = allmax(time.perf_counter() - t0)
+    e2e_value = lups_per_step * e2e_steps / e2e_s / 1e9
+
+    # ---- roofline of the dominant kernel (rank 0, single slab geometry) ----
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        if world == 1:
+            s1 = s
+        else:
+            pb1 = G.make_problem(KERNEL, (NX, NY, NZ), DTYPE)
+            s1 = G.GpuStepper.for_problem(pb1, device=local)
+        T_used = info["tfuse"]
+        ms_pass = s1.time_pass(T_used, reps=20)
+        ms_single = s1.time_pass(1, reps=20)
+        alg_bytes = 2.0 * 8 * NX * NY * NZ          # one read + one write of the grid per launch
+        achieved = alg_bytes / (ms_pass * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(f"k_r1_T{T_used}_fp64_512", None)
+            except Exception:   # noqa: BLE001
+                traffic = None
+        roof = {"bound": "hbm", "kernel": f"k_r1<slot 1, double, T={T_used}> (fused z-streamed sweep)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_pass,
+                "fused_steps_per_launch": T_used,
+                "effective_glups_per_launch": NX * NY * NZ * T_used / (ms_pass * 1e-3) / 1e9,
+                "single_step_pass": {"ms_per_launch": ms_single,
+                                     "achieved": alg_bytes / (ms_single * 1e-3) / 1e9,
+                                     "frac": alg_bytes / (ms_single * 1e-3) / 1e9 / peak}}
+        if world > 1:
+            s1.close()
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                b = run_reference_sample(args.ref_nz, args.ref_nt)
+                cpu_base = {"value": b["glups"], "unit": "GLUP/s", "cores": b["cores"], "kind": b["kind"],
+                            "sample": b["sample"], "seconds": b["seconds"]}
+            except Exception as e:   # noqa: BLE001
+                cpu_base = {"value": None, "unit": "GLUP/s", "cores": host_threads(), "kind": "reference",
+                            "sample": f"failed: {e}"}
+    s.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {"metric": "GLUP/s", "value": value, "unit": "GLUP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_domain": list(gst), "nt": nt_eff, "steps_executed": nsteps,
+                       "stepper": "Diamond (ts 2)", "fused_steps_per_pass": info["tfuse"],
+                       "parallelism": f"z-slab x{world}", "cache": "grid (2 x 1.1 GB per GPU) exceeds the 126 MB L2; no flush needed",
+                       "timing": "cudaEvents on the launching stream inside the C ABI, max over ranks",
+                       "wall_s": wall},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "GLUP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": launches, "roofline": roof}
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tfuse", type=int, default=0)
+    ap.add_argument("--ref-nz", type=int, default=512, help="z extent of the bounded CPU sample")
+    ap.add_argument("--ref-nt", type=int, default=50, help="time steps of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_ours(args)
+
+
+if __name__ == "__main__":
+    main()

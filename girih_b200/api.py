@@ -1,0 +1,238 @@
+"""ctypes mirror of include/girih_cuda.h and of the C host's initialisation.
+
+Names follow the reference's domain: a *problem* is the set of host arrays of one z-slab
+(U1, U2, U3 = roc2, coef) exactly as GIRIH's arrays_allocate / init_coeff / domain_data_fill produce
+them (src/utils.c:153-218, 436-496, 605-697); a *stepper* owns the device copy of one slab and runs
+the time steppers of the reference's TSList[] (src/wrappers.h:29-37).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import lib as _lib
+
+
+class GirihError(RuntimeError):
+    def __init__(self, status: int, what: str, detail: str = ""):
+        self.status = status
+        msg = _lib.cuda().girih_gpu_strerror(status).decode()
+        super().__init__(f"{what}: {msg}" + (f" ({detail})" if detail else ""))
+
+
+@dataclass(frozen=True)
+class KernelDesc:
+    name: str
+    r: int
+    time_order: int
+    nd: int
+    shape: int
+    coeff: int
+    n_coef_arrays: int
+    n_coef_scalars: int
+    words_per_lup: int
+    max_tfuse: int
+    gpu_supported: bool
+
+
+def kernel_info(k: int) -> KernelDesc:
+    d = _lib.KernelDescC()
+    rc = _lib.cuda().girih_kernel_info(k, C.byref(d))
+    if rc:
+        raise GirihError(rc, "girih_kernel_info")
+    return KernelDesc(d.name.decode(), d.r, d.time_order, d.nd, d.shape, d.coeff, d.n_coef_arrays,
+                      d.n_coef_scalars, d.words_per_lup, d.max_tfuse, bool(d.gpu_supported))
+
+
+def gpu_count() -> int:
+    n = C.c_int(0)
+    _lib.cuda().girih_gpu_count(C.byref(n))
+    return n.value
+
+
+def _i3(v):
+    return (C.c_int * 3)(*[int(x) for x in v])
+
+
+def diamond_nt(nt: int, t_dim: int) -> int:
+    """nt after the Diamond stepper's rounding (src/kernels/diamond_utils.c:1042-1056)."""
+    return _lib.host(8).girih_host_diamond_nt(nt, t_dim)
+
+
+@dataclass
+class HostProblem:
+    kernel: int
+    dtype: np.dtype
+    gstencil: tuple      # global interior
+    stencil: tuple       # this slab's interior
+    shape: tuple         # this slab's host array shape (nnx, nny, nnz)
+    gb: tuple            # global begin of this slab
+    rank: int
+    nranks: int
+    r: int
+    U1: np.ndarray       # [nnz, nny, nnx]
+    U2: np.ndarray
+    U3: np.ndarray | None
+    coef: np.ndarray
+
+    def interior(self, a=None):
+        a = self.U1 if a is None else a
+        r = self.r
+        nx, ny, nz = self.stencil
+        return a[r:r + nz, r:r + ny, r:r + nx]
+
+
+def make_problem(kernel, gstencil, dtype=np.float64, rank=0, nranks=1, alignment=8, padding=True,
+                 pinned=False) -> HostProblem:
+    """Host arrays of z-slab `rank`: the C host's init() + init_coeff() + domain_data_fill()."""
+    dtype = np.dtype(dtype)
+    es = dtype.itemsize
+    h = _lib.host(es)
+    info = kernel_info(kernel)
+    ls, ds, gb = (C.c_int * 3)(), (C.c_int * 3)(), (C.c_int * 3)()
+    h.girih_host_shapes(kernel, _i3(gstencil), rank, nranks, alignment, int(padding), ls, ds, gb)
+    shape = tuple(ds)
+    zyx = (shape[2], shape[1], shape[0])
+    ncoef = int(h.girih_host_coef_size(kernel, _i3(gstencil), rank, nranks, alignment, int(padding)))
+
+    def alloc(sh):
+        if pinned:
+            import torch
+            t = torch.empty(sh, dtype=torch.float64 if es == 8 else torch.float32).pin_memory()
+            return t.numpy()
+        return np.empty(sh, dtype)
+
+    U1, U2 = alloc(zyx), alloc(zyx)
+    U3 = alloc(zyx) if info.time_order == 2 else None
+    coef = np.zeros(ncoef, dtype)
+    rc = h.girih_host_fill(kernel, _i3(gstencil), rank, nranks, alignment, int(padding),
+                           U1.ctypes.data, U2.ctypes.data, U3.ctypes.data if U3 is not None else None,
+                           coef.ctypes.data)
+    if rc:
+        raise RuntimeError("girih_host_fill failed")
+    return HostProblem(kernel, dtype, tuple(gstencil), tuple(ls), shape, tuple(gb), rank, nranks, info.r,
+                       U1, U2, U3, coef)
+
+
+class GpuStepper:
+    """Device state of one z-slab + the time steppers (girih_gpu_ctx)."""
+
+    def __init__(self, kernel, stencil, shape, dtype=np.float64, device=0, rank=0, nranks=1):
+        self._lib = _lib.cuda()
+        self._ctx = C.c_void_p()
+        self.kernel, self.dtype = kernel, np.dtype(dtype)
+        self.stencil, self.shape = tuple(stencil), tuple(shape)
+        self.rank, self.nranks = rank, nranks
+        rc = self._lib.girih_gpu_create(C.byref(self._ctx), device, kernel, self.dtype.itemsize,
+                                        _i3(stencil), _i3(shape), rank, nranks)
+        if rc:
+            self._ctx = C.c_void_p()
+            raise GirihError(rc, "girih_gpu_create")
+
+    @classmethod
+    def for_problem(cls, pb: HostProblem, device=0):
+        s = cls(pb.kernel, pb.stencil, pb.shape, pb.dtype, device, pb.rank, pb.nranks)
+        s.upload(pb)
+        return s
+
+    def _check(self, rc, what):
+        if rc:
+            raise GirihError(rc, what, self._lib.girih_gpu_last_error(self._ctx).decode())
+
+    def close(self):
+        if self._ctx:
+            self._lib.girih_gpu_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- communicator -------------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = _lib.cuda().girih_gpu_comm_unique_id(buf, 128)
+        if rc:
+            raise GirihError(rc, "girih_gpu_comm_unique_id")
+        return buf.raw
+
+    def comm_init(self, uid: bytes):
+        self._check(self._lib.girih_gpu_comm_init(self._ctx, uid, len(uid)), "girih_gpu_comm_init")
+
+    # -- transfers ----------------------------------------------------------------------------
+    def upload(self, pb: HostProblem):
+        for a in (pb.U1, pb.U2, pb.U3, pb.coef):
+            assert a is None or (a.dtype == self.dtype and a.flags.c_contiguous)
+        self._check(self._lib.girih_gpu_upload(
+            self._ctx, pb.U1.ctypes.data, pb.U2.ctypes.data,
+            pb.U3.ctypes.data if pb.U3 is not None else None, pb.coef.ctypes.data), "girih_gpu_upload")
+
+    def upload_fields(self, U1, U2):
+        self._check(self._lib.girih_gpu_upload_fields(
+            self._ctx, U1.ctypes.data if U1 is not None else None,
+            U2.ctypes.data if U2 is not None else None), "girih_gpu_upload_fields")
+
+    def download(self, U1=None, U2=None):
+        self._check(self._lib.girih_gpu_download(
+            self._ctx, U1.ctypes.data if U1 is not None else None,
+            U2.ctypes.data if U2 is not None else None), "girih_gpu_download")
+
+    # -- steppers -----------------------------------------------------------------------------
+    def run_single(self, nsteps, overlap=False):
+        self._check(self._lib.girih_gpu_run_single(self._ctx, nsteps, int(overlap)), "girih_gpu_run_single")
+
+    def run_fused(self, nsteps, tfuse=0):
+        self._check(self._lib.girih_gpu_run_fused(self._ctx, nsteps, tfuse), "girih_gpu_run_fused")
+
+    def run_ts(self, ts, nt, t_dim=1, tfuse=0):
+        """The reference CLI's semantics for --target-ts / --nt (returns nt after rounding)."""
+        if ts in (0, 1):
+            self.run_single((nt + 1) // 2 * 2, overlap=(ts == 1))
+            return nt
+        nt = diamond_nt(nt, t_dim)
+        self.run_fused(nt - 1, tfuse)
+        return nt
+
+    def step_box(self, dst, box):
+        self._check(self._lib.girih_gpu_step_box(self._ctx, dst, *[int(b) for b in box]), "girih_gpu_step_box")
+
+    def set_option(self, key, value):
+        self._check(self._lib.girih_gpu_set_option(self._ctx, key.encode(), int(value)), "girih_gpu_set_option")
+
+    def time_pass(self, tfuse, reps=10):
+        """average device milliseconds of one fused pass (= one kernel launch)"""
+        ms = C.c_double()
+        self._check(self._lib.girih_gpu_time_pass(self._ctx, tfuse, reps, C.byref(ms)), "girih_gpu_time_pass")
+        return ms.value
+
+    # -- accounting ---------------------------------------------------------------------------
+    def elapsed_ms(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._lib.girih_gpu_last_elapsed_ms(self._ctx, C.byref(a), C.byref(b), C.byref(c))
+        return {"compute": a.value, "comm": b.value, "total": c.value}
+
+    def launch_info(self):
+        v = [C.c_int() for _ in range(4)]
+        self._lib.girih_gpu_last_launch_info(self._ctx, *[C.byref(x) for x in v])
+        return {"kernels": v[0].value, "passes": v[1].value, "steps": v[2].value, "tfuse": v[3].value}
+
+    def scan_u1(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.girih_gpu_scan_u1(self._ctx, C.byref(a), C.byref(b)), "girih_gpu_scan_u1")
+        return a.value, b.value
+
+
+def run_reference_cli(dtype, args, timeout=3600, env=None):
+    """Run this repo's own mwd_kernel executable (build/ = fp32, build_dp/ = fp64); returns
+    (returncode, stdout, stderr)."""
+    exe = os.path.join(_lib.ROOT, "build_dp" if np.dtype(dtype).itemsize == 8 else "build", "mwd_kernel")
+    out = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=timeout,
+                         env=dict(os.environ, **(env or {})))
+    return out.returncode, out.stdout, out.stderr

@@ -1,0 +1,791 @@
+// girih_cuda.cu -- the C ABI declared in include/girih_cuda.h: context, HBM layout, transfers,
+// time steppers, z-slab halo exchange.  Kernels live in kernels_*.cuh.
+//
+// Built only for sm_100a:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include "../../include/girih_cuda.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_naive.cuh"
+#include "kernels_r1.cuh"
+#include "kernels_r4.cuh"
+#include "nccl_dyn.h"
+#include "stencil_expr.cuh"
+
+using namespace girih;
+
+// ------------------------------------------------------------------------------------------------
+// operator table (stencil_info_list[], src/kernels/stencils.c:260-271)
+// ------------------------------------------------------------------------------------------------
+static const girih_kernel_desc KERNELS[8] = {
+    // name  r to nd shape       coeff                       nca ncs words tfuse gpu
+    {"star", 4, 2, 3, GIRIH_STAR, GIRIH_COEF_CONSTANT, 0, 5, 4, 1, 1},
+    {"star", 1, 1, 2, GIRIH_STAR, GIRIH_COEF_CONSTANT, 0, 2, 2, 4, 1},
+    {"star", 1, 1, 4, GIRIH_STAR, GIRIH_COEF_VARIABLE, 2, 0, 4, 4, 1},
+    {"star", 1, 1, 6, GIRIH_STAR, GIRIH_COEF_VARIABLE_AXSYM, 4, 0, 6, 4, 1},
+    {"star", 4, 1, 15, GIRIH_STAR, GIRIH_COEF_VARIABLE_AXSYM, 13, 0, 15, 1, 1},
+    {"star", 1, 1, 9, GIRIH_STAR, GIRIH_COEF_VARIABLE_NOSYM, 7, 0, 9, 4, 1},
+    {"star", 1, 1, 40, GIRIH_STAR, GIRIH_COEF_SOLAR, 0, 0, 40, 1, 0},
+    {"box", 1, 1, 2, GIRIH_BOX, GIRIH_COEF_CONSTANT, 0, 4, 2, 1, 1},
+};
+
+extern "C" int girih_kernel_count(void) { return 8; }
+extern "C" int girih_kernel_info(int k, girih_kernel_desc *out) {
+  if (k < 0 || k >= 8 || out == nullptr) return GIRIH_ERR_ARG;
+  *out = KERNELS[k];
+  return GIRIH_OK;
+}
+
+extern "C" const char *girih_gpu_strerror(int s) {
+  switch (s) {
+    case GIRIH_OK: return "success";
+    case GIRIH_ERR_ARG: return "invalid argument";
+    case GIRIH_ERR_NO_DEVICE: return "no CUDA device available (this library has no CPU fallback)";
+    case GIRIH_ERR_CUDA: return "CUDA runtime error";
+    case GIRIH_ERR_UNSUPPORTED: return "unsupported configuration for the selected stencil";
+    case GIRIH_ERR_NCCL: return "NCCL error";
+    case GIRIH_ERR_STATE: return "invalid call order";
+    case GIRIH_ERR_FRAME: return "fused stepping requires identical boundary frames in U1 and U2";
+    default: return "unknown error";
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct EvPair { cudaEvent_t a, b; };
+
+struct girih_gpu_ctx {
+  int device = 0, kernel = 0, es = 8, rank = 0, nranks = 1;
+  int hshape[3] = {0, 0, 0};   // host array shape
+  int st[3] = {0, 0, 0};       // local interior
+  girih_kernel_desc kd{};
+  DevGrid g{};
+  size_t arr_elems = 0;
+  int halo_max = 0;            // deepest z halo the allocation supports (planes)
+  void *dU[2] = {nullptr, nullptr};   // [0] = U1, [1] = U2
+  void *dU3 = nullptr, *dCoef = nullptr;
+  double cc[5] = {0, 0, 0, 0, 0};
+  cudaStream_t s_comp = nullptr, s_comm = nullptr;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_x = nullptr, ev_y = nullptr;
+  std::vector<EvPair> comm_ev;
+  size_t comm_ev_used = 0;
+  bool uploaded = false, frames_equal = true, static_halo_done = false;
+  // NCCL
+  ncclComm_t comm = nullptr;
+  // options
+  int opt_variant = 0, opt_zchunk = 0, opt_tile = 0, opt_overlap = 1;
+  // accounting of the last run
+  double ms_compute = 0, ms_comm = 0, ms_total = 0;
+  int n_kernels = 0, n_passes = 0, n_steps = 0, tfuse_used = 1;
+  unsigned long long *d_scan = nullptr;
+  char err[512] = "";
+};
+
+static int fail(girih_gpu_ctx *c, int status, const char *fmt, ...) {
+  if (c) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c->err, sizeof(c->err), fmt, ap);
+    va_end(ap);
+  }
+  return status;
+}
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(c, GIRIH_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),  \
+                  __FILE__, __LINE__);                                                        \
+  } while (0)
+#define NC(call)                                                                              \
+  do {                                                                                        \
+    ncclResult_t r_ = (call);                                                                 \
+    if (r_ != ncclSuccess)                                                                    \
+      return fail(c, GIRIH_ERR_NCCL, "%s failed: %s (%s:%d)", #call,                          \
+                  nccl_dyn()->GetErrorString(r_), __FILE__, __LINE__);                        \
+  } while (0)
+
+extern "C" const char *girih_gpu_last_error(girih_gpu_ctx *c) { return c ? c->err : ""; }
+
+extern "C" int girih_gpu_count(int *n) {
+  int k = 0;
+  cudaError_t e = cudaGetDeviceCount(&k);
+  if (n) *n = (e == cudaSuccess) ? k : 0;
+  if (e != cudaSuccess || k == 0) return GIRIH_ERR_NO_DEVICE;
+  return GIRIH_OK;
+}
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+extern "C" int girih_gpu_create(girih_gpu_ctx **out, int device, int target_kernel, int elem_size,
+                                const int st[3], const int ds[3], int rank, int nranks) {
+  if (!out || !st || !ds) return GIRIH_ERR_ARG;
+  *out = nullptr;
+  if (target_kernel < 0 || target_kernel >= 8) return GIRIH_ERR_ARG;
+  if (elem_size != 4 && elem_size != 8) return GIRIH_ERR_ARG;
+  if (!KERNELS[target_kernel].gpu_supported) return GIRIH_ERR_UNSUPPORTED;
+  if (nranks < 1 || rank < 0 || rank >= nranks) return GIRIH_ERR_ARG;
+  const int r = KERNELS[target_kernel].r;
+  if (st[0] < 1 || st[1] < 1 || st[2] < 1) return GIRIH_ERR_ARG;
+  if (ds[0] < st[0] + 2 * r || ds[1] != st[1] + 2 * r || ds[2] != st[2] + 2 * r) return GIRIH_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return GIRIH_ERR_NO_DEVICE;
+  if (device < 0 || device >= ndev) return GIRIH_ERR_ARG;
+
+  girih_gpu_ctx *c = new girih_gpu_ctx();
+  c->device = device; c->kernel = target_kernel; c->es = elem_size; c->rank = rank; c->nranks = nranks;
+  c->kd = KERNELS[target_kernel];
+  for (int d = 0; d < 3; ++d) { c->hshape[d] = ds[d]; c->st[d] = st[d]; }
+  auto bail = [&](int status) { girih_gpu_destroy(c); return status; };
+  if (cudaSetDevice(device) != cudaSuccess) return bail(GIRIH_ERR_CUDA);
+
+  // HBM layout (see DevGrid): interior x origin 128-byte aligned, rows padded to 128 bytes plus one
+  // spare 128-byte group so that the last (partial) tile's vector accesses stay inside the row.
+  const int epl = 128 / elem_size;            // elements per 128 bytes
+  const int guard = c->kd.max_tfuse * r;      // deepest halo / overlap any stepper uses
+  DevGrid &g = c->g;
+  g.r = r; g.nx = st[0]; g.ny = st[1]; g.nz = st[2];
+  g.X0 = epl;                                 // >= guard, keeps x = X0 line aligned
+  g.Y0 = std::max(guard, r);
+  g.Z0 = std::max(guard, r);
+  g.px = round_up(g.X0 + g.nx + std::max(guard, r), epl) + epl;
+  g.ny_dev = g.Y0 + g.ny + std::max(guard, r);
+  g.nz_dev = g.Z0 + g.nz + std::max(guard, r);
+  g.pxy = (long long)g.px * g.ny_dev;
+  g.zlo = (rank == 0) ? g.Z0 : -(1 << 30);
+  g.zhi = (rank == nranks - 1) ? g.Z0 + g.nz : (1 << 30);
+  c->halo_max = std::max(guard, r);
+  c->arr_elems = (size_t)g.pxy * g.nz_dev;
+  if (nranks > 1 && g.nz < c->halo_max) {
+    fail(c, GIRIH_ERR_ARG, "slab of %d planes is thinner than the deepest halo (%d)", g.nz, c->halo_max);
+    return bail(GIRIH_ERR_ARG);
+  }
+
+  const size_t bytes = c->arr_elems * elem_size;
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaMalloc(&c->dU[i], bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->dU[i], 0, bytes);
+  }
+  if (e == cudaSuccess && c->kd.time_order == 2) {
+    e = cudaMalloc(&c->dU3, bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->dU3, 0, bytes);
+  }
+  if (e == cudaSuccess && c->kd.n_coef_arrays > 0) {
+    e = cudaMalloc(&c->dCoef, bytes * c->kd.n_coef_arrays);
+    if (e == cudaSuccess) e = cudaMemset(c->dCoef, 0, bytes * c->kd.n_coef_arrays);
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_scan, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&c->ev_t0);
+  if (e == cudaSuccess) e = cudaEventCreate(&c->ev_t1);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_y, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "girih_gpu_create: %s\n", cudaGetErrorString(e));
+    return bail(GIRIH_ERR_CUDA);
+  }
+  *out = c;
+  return GIRIH_OK;
+}
+
+extern "C" void girih_gpu_destroy(girih_gpu_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->s_comp) cudaStreamSynchronize(c->s_comp);
+  if (c->s_comm) cudaStreamSynchronize(c->s_comm);
+  if (c->comm && nccl_dyn()) nccl_dyn()->CommDestroy(c->comm);
+  for (int i = 0; i < 2; ++i) if (c->dU[i]) cudaFree(c->dU[i]);
+  if (c->dU3) cudaFree(c->dU3);
+  if (c->dCoef) cudaFree(c->dCoef);
+  if (c->d_scan) cudaFree(c->d_scan);
+  for (auto &p : c->comm_ev) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+  if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+  if (c->ev_x) cudaEventDestroy(c->ev_x);
+  if (c->ev_y) cudaEventDestroy(c->ev_y);
+  if (c->s_comp) cudaStreamDestroy(c->s_comp);
+  if (c->s_comm) cudaStreamDestroy(c->s_comm);
+  delete c;
+}
+
+extern "C" int girih_gpu_set_option(girih_gpu_ctx *c, const char *key, int value) {
+  if (!c || !key) return GIRIH_ERR_ARG;
+  if (!strcmp(key, "variant")) c->opt_variant = value;
+  else if (!strcmp(key, "zchunk")) c->opt_zchunk = value;
+  else if (!strcmp(key, "tile")) c->opt_tile = value;
+  else if (!strcmp(key, "overlap")) c->opt_overlap = value;
+  else return fail(c, GIRIH_ERR_ARG, "unknown option '%s'", key);
+  return GIRIH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// transfers
+// ------------------------------------------------------------------------------------------------
+// host array (reference layout, hshape) <-> device array (DevGrid layout); all planes of the host
+// array are moved, i.e. the interior plus the r-deep frame / inter-slab halo.
+static cudaError_t copy3d(girih_gpu_ctx *c, void *dev, const void *host_c, bool to_device,
+                          cudaStream_t s, bool async) {
+  const DevGrid &g = c->g;
+  const int r = g.r, es = c->es;
+  void *host = const_cast<void *>(host_c);
+  cudaMemcpy3DParms p;
+  memset(&p, 0, sizeof(p));
+  cudaPitchedPtr hp = make_cudaPitchedPtr(host, (size_t)c->hshape[0] * es, c->hshape[0], c->hshape[1]);
+  cudaPitchedPtr dp = make_cudaPitchedPtr(dev, (size_t)g.px * es, g.px, g.ny_dev);
+  cudaPos hpos = make_cudaPos(0, 0, 0);
+  cudaPos dpos = make_cudaPos((size_t)(g.X0 - r) * es, g.Y0 - r, g.Z0 - r);
+  p.extent = make_cudaExtent((size_t)(g.nx + 2 * r) * es, c->hshape[1], c->hshape[2]);
+  if (to_device) { p.srcPtr = hp; p.srcPos = hpos; p.dstPtr = dp; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
+  else           { p.srcPtr = dp; p.srcPos = dpos; p.dstPtr = hp; p.dstPos = hpos; p.kind = cudaMemcpyDeviceToHost; }
+  return async ? cudaMemcpy3DAsync(&p, s) : cudaMemcpy3D(&p);
+}
+
+template <typename R>
+static bool frames_match(const girih_gpu_ctx *c, const R *a, const R *b) {
+  // true iff U1 and U2 agree on every cell the steppers never write: the Dirichlet frame
+  // (not the halo planes between slabs, which are interior points of the global domain)
+  const int nnx = c->hshape[0], nny = c->hshape[1], nnz = c->hshape[2], r = c->g.r;
+  const int nx = c->st[0];
+  const bool zfirst = c->rank == 0, zlast = c->rank == c->nranks - 1;
+  for (int k = 0; k < nnz; ++k) {
+    const bool kframe = (zfirst && k < r) || (zlast && k >= nnz - r);
+    for (int j = 0; j < nny; ++j) {
+      const bool jframe = (j < r) || (j >= nny - r);
+      const size_t row = ((size_t)k * nny + j) * nnx;
+      if (kframe || jframe) {
+        if (memcmp(a + row, b + row, sizeof(R) * (size_t)(nx + 2 * r)) != 0) return false;
+      } else {
+        if (memcmp(a + row, b + row, sizeof(R) * r) != 0) return false;
+        if (memcmp(a + row + nx + r, b + row + nx + r, sizeof(R) * r) != 0) return false;
+      }
+    }
+  }
+  return true;
+}
+
+extern "C" int girih_gpu_upload(girih_gpu_ctx *c, const void *U1, const void *U2, const void *U3,
+                                const void *coef) {
+  if (!c || !U1 || !U2) return GIRIH_ERR_ARG;
+  if (c->kd.time_order == 2 && !U3) return fail(c, GIRIH_ERR_ARG, "U3 (roc2) is required for time_order 2");
+  if ((c->kd.n_coef_arrays > 0 || c->kd.n_coef_scalars > 0) && !coef) return fail(c, GIRIH_ERR_ARG, "coef is required");
+  CU(cudaSetDevice(c->device));
+  CU(copy3d(c, c->dU[0], U1, true, 0, false));
+  CU(copy3d(c, c->dU[1], U2, true, 0, false));
+  if (c->kd.time_order == 2) CU(copy3d(c, c->dU3, U3, true, 0, false));
+  const size_t ln = (size_t)c->hshape[0] * c->hshape[1] * c->hshape[2];
+  for (int m = 0; m < c->kd.n_coef_arrays; ++m)
+    CU(copy3d(c, (char *)c->dCoef + (size_t)m * c->arr_elems * c->es,
+              (const char *)coef + (size_t)m * ln * c->es, true, 0, false));
+  for (int m = 0; m < c->kd.n_coef_scalars; ++m)
+    c->cc[m] = (c->es == 8) ? ((const double *)coef)[m] : (double)((const float *)coef)[m];
+  c->frames_equal = (c->es == 8) ? frames_match(c, (const double *)U1, (const double *)U2)
+                                 : frames_match(c, (const float *)U1, (const float *)U2);
+  c->uploaded = true;
+  c->static_halo_done = false;
+  return GIRIH_OK;
+}
+
+extern "C" int girih_gpu_upload_fields(girih_gpu_ctx *c, const void *U1, const void *U2) {
+  if (!c || !c->uploaded) return fail(c, GIRIH_ERR_STATE, "upload_fields before upload");
+  CU(cudaSetDevice(c->device));
+  if (U1) CU(copy3d(c, c->dU[0], U1, true, c->s_comp, true));
+  if (U2) CU(copy3d(c, c->dU[1], U2, true, c->s_comp, true));
+  CU(cudaStreamSynchronize(c->s_comp));
+  return GIRIH_OK;
+}
+
+extern "C" int girih_gpu_download(girih_gpu_ctx *c, void *U1, void *U2) {
+  if (!c) return GIRIH_ERR_ARG;
+  if (!c->uploaded) return fail(c, GIRIH_ERR_STATE, "download before upload");
+  CU(cudaSetDevice(c->device));
+  if (U1) CU(copy3d(c, U1, c->dU[0], false, c->s_comp, true));
+  if (U2) CU(copy3d(c, U2, c->dU[1], false, c->s_comp, true));
+  CU(cudaStreamSynchronize(c->s_comp));
+  return GIRIH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL bootstrap and halo exchange
+// ------------------------------------------------------------------------------------------------
+extern "C" int girih_gpu_comm_unique_id(void *id, size_t len) {
+  if (!id || len < GIRIH_COMM_ID_BYTES) return GIRIH_ERR_ARG;
+  if (!nccl_dyn()) return GIRIH_ERR_NCCL;
+  ncclUniqueId uid;
+  if (nccl_dyn()->GetUniqueId(&uid) != ncclSuccess) return GIRIH_ERR_NCCL;
+  static_assert(sizeof(ncclUniqueId) <= GIRIH_COMM_ID_BYTES, "id size");
+  memset(id, 0, len);
+  memcpy(id, &uid, sizeof(uid));
+  return GIRIH_OK;
+}
+
+extern "C" int girih_gpu_comm_init(girih_gpu_ctx *c, const void *id, size_t len) {
+  if (!c || !id || len < sizeof(ncclUniqueId)) return GIRIH_ERR_ARG;
+  if (c->nranks == 1) return GIRIH_OK;
+  if (!nccl_dyn()) return fail(c, GIRIH_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", nccl_dyn_error());
+  CU(cudaSetDevice(c->device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  NC(nccl_dyn()->CommInitRank(&c->comm, c->nranks, uid, c->rank));
+  return GIRIH_OK;
+}
+
+// Exchange `depth` planes of `arr` with both z neighbours on the comm stream: my top `depth`
+// interior planes go to the upper neighbour's lower halo and vice versa (geometry of
+// src/mpi_utils.c:173-200 generalised from r to depth = T*r planes).  Planes are contiguous,
+// so no pack/unpack kernel is needed.
+static int exchange_z(girih_gpu_ctx *c, void *arr, int depth, cudaStream_t s) {
+  if (c->nranks == 1) return GIRIH_OK;
+  if (!c->comm) return fail(c, GIRIH_ERR_STATE, "girih_gpu_comm_init was not called");
+  const DevGrid &g = c->g;
+  const size_t plane_b = (size_t)g.pxy * c->es;
+  const size_t count = (size_t)depth * plane_b;
+  char *base = (char *)arr;
+  const int up = c->rank + 1, dn = c->rank - 1;
+  NC(nccl_dyn()->GroupStart());
+  if (dn >= 0) {
+    NC(nccl_dyn()->Send(base + (size_t)g.Z0 * plane_b, count, ncclChar, dn, c->comm, s));
+    NC(nccl_dyn()->Recv(base + (size_t)(g.Z0 - depth) * plane_b, count, ncclChar, dn, c->comm, s));
+  }
+  if (up < c->nranks) {
+    NC(nccl_dyn()->Send(base + (size_t)(g.Z0 + g.nz - depth) * plane_b, count, ncclChar, up, c->comm, s));
+    NC(nccl_dyn()->Recv(base + (size_t)(g.Z0 + g.nz) * plane_b, count, ncclChar, up, c->comm, s));
+  }
+  NC(nccl_dyn()->GroupEnd());
+  return GIRIH_OK;
+}
+
+static int timed_exchange(girih_gpu_ctx *c, void *arr, int depth) {
+  // runs on the comm stream, ordered after everything issued so far on the compute stream, and
+  // makes the compute stream wait for its completion
+  if (c->nranks == 1) return GIRIH_OK;
+  if (c->comm_ev_used == c->comm_ev.size()) {
+    EvPair p;
+    CU(cudaEventCreate(&p.a));
+    CU(cudaEventCreate(&p.b));
+    c->comm_ev.push_back(p);
+  }
+  EvPair &p = c->comm_ev[c->comm_ev_used++];
+  CU(cudaEventRecord(c->ev_x, c->s_comp));
+  CU(cudaStreamWaitEvent(c->s_comm, c->ev_x, 0));
+  CU(cudaEventRecord(p.a, c->s_comm));
+  int rc = exchange_z(c, arr, depth, c->s_comm);
+  if (rc) return rc;
+  CU(cudaEventRecord(p.b, c->s_comm));
+  CU(cudaStreamWaitEvent(c->s_comp, p.b, 0));
+  return GIRIH_OK;
+}
+
+// time-invariant arrays (roc2, per-point coefficients) need their deep halos once
+static int exchange_static(girih_gpu_ctx *c) {
+  if (c->nranks == 1 || c->static_halo_done) return GIRIH_OK;
+  int rc = 0;
+  if (c->dU3 && (rc = timed_exchange(c, c->dU3, c->halo_max))) return rc;
+  for (int m = 0; m < c->kd.n_coef_arrays; ++m)
+    if ((rc = timed_exchange(c, (char *)c->dCoef + (size_t)m * c->arr_elems * c->es, c->halo_max))) return rc;
+  c->static_halo_done = true;
+  return GIRIH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------------------------------
+template <typename R> static ConstCoef<R> make_cc(const girih_gpu_ctx *c) {
+  ConstCoef<R> k;
+  for (int i = 0; i < 5; ++i) k.v[i] = (R)c->cc[i];
+  return k;
+}
+
+// ---- naive: one step over a device-coordinate box -------------------------------------------
+template <int K, typename R>
+static cudaError_t launch_naive_t(girih_gpu_ctx *c, int dst, int xb, int yb, int zb, int xe, int ye, int ze) {
+  if (xe <= xb || ye <= yb || ze <= zb) return cudaSuccess;
+  dim3 block(64, 4, 1);
+  dim3 grid((xe - xb + 63) / 64, (ye - yb + 3) / 4, ze - zb);
+  R *u = (R *)c->dU[dst];
+  const R *v = (const R *)c->dU[dst ^ 1];
+  k_naive<K, R><<<grid, block, 0, c->s_comp>>>(c->g, u, v, (const R *)c->dU3, (const R *)c->dCoef,
+                                              (long long)c->arr_elems, make_cc<R>(c), xb, yb, zb, xe, ye, ze);
+  c->n_kernels++;
+  return cudaGetLastError();
+}
+static cudaError_t launch_naive(girih_gpu_ctx *c, int dst, int xb, int yb, int zb, int xe, int ye, int ze) {
+#define GN(K)                                                                          \
+  case K:                                                                              \
+    return c->es == 8 ? launch_naive_t<K, double>(c, dst, xb, yb, zb, xe, ye, ze)      \
+                      : launch_naive_t<K, float>(c, dst, xb, yb, zb, xe, ye, ze);
+  switch (c->kernel) { GN(0) GN(1) GN(2) GN(3) GN(4) GN(5) GN(7) default: return cudaErrorInvalidValue; }
+#undef GN
+}
+
+// ---- radius-1 streamed / fused ----------------------------------------------------------------
+struct TileChoice { int py, nw; };
+
+template <int K, typename R, int T, int PY, int NW>
+static cudaError_t launch_r1_t(girih_gpu_ctx *c, int src, int dst, int zb0, int ze0) {
+  using Cfg = R1Cfg<R, T, PY, NW>;
+  const DevGrid &g = c->g;
+  R1Args<R> a;
+  a.g = g;
+  a.in = (const R *)c->dU[src];
+  a.out = (R *)c->dU[dst];
+  a.coef = (const R *)c->dCoef;
+  a.coef_stride = (long long)c->arr_elems;
+  a.cc = make_cc<R>(c);
+  a.zb0 = zb0; a.ze0 = ze0;
+  const int ntx = (g.nx + Cfg::UX - 1) / Cfg::UX, nty = (g.ny + Cfg::UY - 1) / Cfg::UY;
+  int zchunk = c->opt_zchunk;
+  if (zchunk <= 0) {
+    // aim for >= ~6 waves of CTAs over 148 SMs while keeping the 2T-plane pipeline fill per chunk small
+    const int nz = ze0 - zb0;
+    const int want = 148 * 6;
+    int nch = std::max(1, (want + ntx * nty - 1) / (ntx * nty));
+    zchunk = std::max(std::min(nz, 16 * T), (nz + nch - 1) / nch);
+  }
+  a.zchunk = zchunk;
+  dim3 grid(ntx, nty, (ze0 - zb0 + zchunk - 1) / zchunk);
+  auto kfn = k_r1<K, R, T, PY, NW>;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  if (e != cudaSuccess) return e;
+  kfn<<<grid, 32 * NW, Cfg::SMEM, c->s_comp>>>(a);
+  c->n_kernels++;
+  return cudaGetLastError();
+}
+
+template <int K, typename R, int T>
+static cudaError_t launch_r1_tile(girih_gpu_ctx *c, int src, int dst, int zb0, int ze0) {
+  // tile shapes instantiated per (operator, precision, depth); "tile" option = PY*100 + NW
+  const int tile = c->opt_tile;
+  if constexpr (KTraits<K>::NCA == 0) {
+    if (tile == 216) return launch_r1_t<K, R, T, 2, 16>(c, src, dst, zb0, ze0);
+    if (tile == 412) return launch_r1_t<K, R, T, 4, 12>(c, src, dst, zb0, ze0);
+    return launch_r1_t<K, R, T, 4, 8>(c, src, dst, zb0, ze0);
+  } else {
+    if (tile == 408) return launch_r1_t<K, R, T, 4, 8>(c, src, dst, zb0, ze0);
+    return launch_r1_t<K, R, T, 2, 16>(c, src, dst, zb0, ze0);
+  }
+}
+
+template <int K, typename R>
+static cudaError_t launch_r1_depth(girih_gpu_ctx *c, int T, int src, int dst, int zb0, int ze0) {
+  switch (T) {
+    case 1: return launch_r1_tile<K, R, 1>(c, src, dst, zb0, ze0);
+    case 2: return launch_r1_tile<K, R, 2>(c, src, dst, zb0, ze0);
+    case 3: return launch_r1_tile<K, R, 3>(c, src, dst, zb0, ze0);
+    case 4: return launch_r1_tile<K, R, 4>(c, src, dst, zb0, ze0);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ---- radius-4 streamed --------------------------------------------------------------------------
+template <int K, typename R, int PY, int NW>
+static cudaError_t launch_r4_t(girih_gpu_ctx *c, int src, int dst, int zb0, int ze0) {
+  using Cfg = R4Cfg<R, PY, NW>;
+  const DevGrid &g = c->g;
+  R4Args<R> a;
+  a.g = g;
+  a.v = (const R *)c->dU[src];
+  a.u = (R *)c->dU[dst];
+  a.roc2 = (const R *)c->dU3;
+  a.coef = (const R *)c->dCoef;
+  a.coef_stride = (long long)c->arr_elems;
+  a.cc = make_cc<R>(c);
+  a.zb0 = zb0; a.ze0 = ze0;
+  const int ntx = (g.nx + Cfg::WX - 1) / Cfg::WX, nty = (g.ny + Cfg::H - 1) / Cfg::H;
+  int zchunk = c->opt_zchunk;
+  if (zchunk <= 0) {
+    const int nz = ze0 - zb0;
+    const int want = 148 * 8;
+    int nch = std::max(1, (want + ntx * nty - 1) / (ntx * nty));
+    zchunk = std::max(std::min(nz, 32), (nz + nch - 1) / nch);
+  }
+  a.zchunk = zchunk;
+  dim3 grid(ntx, nty, (ze0 - zb0 + zchunk - 1) / zchunk);
+  auto kfn = k_r4<K, R, PY, NW>;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  if (e != cudaSuccess) return e;
+  kfn<<<grid, 32 * NW, Cfg::SMEM, c->s_comp>>>(a);
+  c->n_kernels++;
+  return cudaGetLastError();
+}
+
+// One fused pass: T steps reading array `src` and writing array `dst` (src != dst) on the output
+// planes [zb0, ze0) (device z).  T == 1 is the single step of ts 0/1.
+static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb0, int ze0) {
+  const DevGrid &g = c->g;
+  if (ze0 <= zb0) return cudaSuccess;
+  const bool streamed = (c->opt_variant != 1);
+  if (!streamed || c->kernel == 7) {
+    if (T != 1) return cudaErrorInvalidValue;
+    return launch_naive(c, dst, g.X0, g.Y0, zb0, g.X0 + g.nx, g.Y0 + g.ny, ze0);
+  }
+#define R1(K)                                                                              \
+  case K:                                                                                  \
+    return c->es == 8 ? launch_r1_depth<K, double>(c, T, src, dst, zb0, ze0)               \
+                      : launch_r1_depth<K, float>(c, T, src, dst, zb0, ze0);
+#define R4(K)                                                                              \
+  case K:                                                                                  \
+    if (T != 1) return cudaErrorInvalidValue;                                              \
+    return c->es == 8 ? launch_r4_t<K, double, 2, 8>(c, src, dst, zb0, ze0)                \
+                      : launch_r4_t<K, float, 2, 8>(c, src, dst, zb0, ze0);
+  switch (c->kernel) { R4(0) R1(1) R1(2) R1(3) R4(4) R1(5) default: return cudaErrorInvalidValue; }
+#undef R1
+#undef R4
+}
+
+// ------------------------------------------------------------------------------------------------
+// steppers
+// ------------------------------------------------------------------------------------------------
+static int begin_run(girih_gpu_ctx *c) {
+  if (!c->uploaded) return fail(c, GIRIH_ERR_STATE, "run before upload");
+  CU(cudaSetDevice(c->device));
+  c->n_kernels = c->n_passes = c->n_steps = 0;
+  c->comm_ev_used = 0;
+  c->ms_compute = c->ms_comm = c->ms_total = 0;
+  CU(cudaEventRecord(c->ev_t0, c->s_comp));
+  return GIRIH_OK;
+}
+static int end_run(girih_gpu_ctx *c) {
+  CU(cudaEventRecord(c->ev_t1, c->s_comp));
+  CU(cudaStreamSynchronize(c->s_comp));
+  CU(cudaStreamSynchronize(c->s_comm));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+  c->ms_total = ms;
+  double comm = 0;
+  for (size_t i = 0; i < c->comm_ev_used; ++i) {
+    float m = 0;
+    CU(cudaEventElapsedTime(&m, c->comm_ev[i].a, c->comm_ev[i].b));
+    comm += m;
+  }
+  c->ms_comm = comm;
+  c->ms_compute = c->ms_total;   // kernels run back to back on the compute stream
+  return GIRIH_OK;
+}
+
+// Runs the passes in `sizes` (steps per pass) back to back over all local interior planes.  Every
+// pass reads the array holding the newest level (`cur`) and writes the other one.
+// overlap: the planes the neighbours need for the NEXT pass are computed first and their exchange
+// runs on the comm stream underneath the rest of the pass (the halo-first pattern,
+// src/kernels/halo_first_ts.c:156-194, with depth T*r instead of r).
+static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur, bool overlap) {
+  const DevGrid &g = c->g;
+  const int r = g.r;
+  const int zb = g.Z0, ze = g.Z0 + g.nz;
+  int ready = 0;   // depth of valid halo planes already present around array `cur`
+  int rc;
+  for (size_t p = 0; p < sizes.size(); ++p) {
+    const int T = sizes[p];
+    const int src = cur, dst = cur ^ 1;
+    if (c->nranks > 1 && ready < T * r) {
+      if ((rc = timed_exchange(c, c->dU[src], T * r))) return rc;
+    }
+    const int nd = (p + 1 < sizes.size()) ? sizes[p + 1] * r : r;   // halo depth the next pass needs
+    if (overlap && c->nranks > 1 && g.nz >= 4 * nd) {
+      CU(launch_pass(c, T, src, dst, zb, zb + nd));
+      CU(launch_pass(c, T, src, dst, ze - nd, ze));
+      CU(cudaEventRecord(c->ev_y, c->s_comp));
+      CU(cudaStreamWaitEvent(c->s_comm, c->ev_y, 0));
+      if (c->comm_ev_used == c->comm_ev.size()) {
+        EvPair q;
+        CU(cudaEventCreate(&q.a));
+        CU(cudaEventCreate(&q.b));
+        c->comm_ev.push_back(q);
+      }
+      EvPair &q = c->comm_ev[c->comm_ev_used++];
+      CU(cudaEventRecord(q.a, c->s_comm));
+      if ((rc = exchange_z(c, c->dU[dst], nd, c->s_comm))) return rc;
+      CU(cudaEventRecord(q.b, c->s_comm));
+      CU(launch_pass(c, T, src, dst, zb + nd, ze - nd));
+      CU(cudaStreamWaitEvent(c->s_comp, q.b, 0));
+      ready = nd;
+    } else {
+      CU(launch_pass(c, T, src, dst, zb, ze));
+      ready = 0;
+    }
+    cur = dst;
+    c->n_passes++;
+    c->n_steps += T;
+  }
+  return GIRIH_OK;
+}
+
+static int finish_halos(girih_gpu_ctx *c) {
+  // leave both arrays with exchanged r-deep halos, as the reference's steppers do
+  // (src/kernels/nb_naive_ts.c:192,198)
+  if (c->nranks == 1) return GIRIH_OK;
+  int rc;
+  if ((rc = timed_exchange(c, c->dU[0], c->g.r))) return rc;
+  if ((rc = timed_exchange(c, c->dU[1], c->g.r))) return rc;
+  return GIRIH_OK;
+}
+
+extern "C" int girih_gpu_run_single(girih_gpu_ctx *c, int nsteps, int overlap) {
+  if (!c || nsteps < 0) return GIRIH_ERR_ARG;
+  int rc;
+  if ((rc = begin_run(c))) return rc;
+  if ((rc = exchange_static(c))) return rc;
+  std::vector<int> sizes((size_t)nsteps, 1);
+  int cur = 1;   // level 0 is read from U2 by step 1 (src/kernels/nb_naive_ts.c:189)
+  if ((rc = run_passes(c, sizes, cur, overlap != 0))) return rc;
+  if ((rc = finish_halos(c))) return rc;
+  c->tfuse_used = 1;
+  return end_run(c);
+}
+
+extern "C" int girih_gpu_run_fused(girih_gpu_ctx *c, int nsteps, int tfuse) {
+  if (!c || nsteps < 0) return GIRIH_ERR_ARG;
+  int T = tfuse;
+  if (T <= 0) T = c->kd.max_tfuse;
+  T = std::min(T, c->kd.max_tfuse);
+  if (c->opt_variant == 1 || c->kernel == 7) T = 1;
+  if (c->nranks > 1) T = std::min(T, std::max(1, c->g.nz / std::max(1, c->g.r)));
+  if (T > 1 && !c->frames_equal) return fail(c, GIRIH_ERR_FRAME, "%s", girih_gpu_strerror(GIRIH_ERR_FRAME));
+  int rc;
+  if ((rc = begin_run(c))) return rc;
+  if ((rc = exchange_static(c))) return rc;
+  // All but the last step are fused; the last one is a single step so that BOTH arrays end up
+  // holding the levels the reference leaves (newest and newest-1).  Every pass moves the newest
+  // level to the other array, and level n must end in U1 when n is odd: the number of passes that
+  // cover the first nsteps-1 steps must have the parity of nsteps-1.
+  std::vector<int> sizes;
+  if (nsteps > 0) {
+    int n1 = nsteps - 1;
+    while (n1 >= T) { sizes.push_back(T); n1 -= T; }
+    if (n1 > 0) sizes.push_back(n1);
+    if (((int)sizes.size() - (nsteps - 1)) % 2 != 0) {
+      // some pass has >= 2 steps here (otherwise the count equals the step count): split it
+      for (size_t i = sizes.size(); i-- > 0;)
+        if (sizes[i] >= 2) {
+          const int a1 = sizes[i] / 2, a2 = sizes[i] - a1;
+          sizes[i] = a2;
+          sizes.insert(sizes.begin() + (long)i + 1, a1);
+          break;
+        }
+    }
+    sizes.push_back(1);
+  }
+  int cur = 1;
+  if ((rc = run_passes(c, sizes, cur, c->opt_overlap != 0))) return rc;
+  if (nsteps > 0 && cur != ((nsteps % 2 == 1) ? 0 : 1))
+    return fail(c, GIRIH_ERR_STATE, "internal: pass schedule left the newest level in the wrong array");
+  if ((rc = finish_halos(c))) return rc;
+  c->tfuse_used = T;
+  return end_run(c);
+}
+
+extern "C" int girih_gpu_step_box(girih_gpu_ctx *c, int dst, int xb, int yb, int zb, int xe, int ye, int ze) {
+  if (!c || (dst != 1 && dst != 2)) return GIRIH_ERR_ARG;
+  if (!c->uploaded) return fail(c, GIRIH_ERR_STATE, "step_box before upload");
+  const DevGrid &g = c->g;
+  const int r = g.r;
+  if (xb < r || yb < r || zb < r || xe > g.nx + r || ye > g.ny + r || ze > g.nz + r)
+    return fail(c, GIRIH_ERR_ARG, "box must lie inside the interior");
+  CU(cudaSetDevice(c->device));
+  CU(launch_naive(c, dst - 1, xb - r + g.X0, yb - r + g.Y0, zb - r + g.Z0, xe - r + g.X0, ye - r + g.Y0,
+                  ze - r + g.Z0));
+  CU(cudaStreamSynchronize(c->s_comp));
+  return GIRIH_OK;
+}
+
+extern "C" int girih_gpu_time_pass(girih_gpu_ctx *c, int tfuse, int reps, double *ms_per_pass) {
+  if (!c || reps < 1 || !ms_per_pass) return GIRIH_ERR_ARG;
+  if (!c->uploaded) return fail(c, GIRIH_ERR_STATE, "time_pass before upload");
+  if (c->nranks != 1) return fail(c, GIRIH_ERR_ARG, "time_pass works on single-slab contexts");
+  int T = std::max(1, std::min(tfuse, c->kd.max_tfuse));
+  if (c->opt_variant == 1 || c->kernel == 7) T = 1;
+  if (T > 1 && !c->frames_equal) return fail(c, GIRIH_ERR_FRAME, "%s", girih_gpu_strerror(GIRIH_ERR_FRAME));
+  CU(cudaSetDevice(c->device));
+  c->n_kernels = 0;
+  const DevGrid &g = c->g;
+  int cur = 1;
+  CU(launch_pass(c, T, cur, cur ^ 1, g.Z0, g.Z0 + g.nz));   // warm
+  cur ^= 1;
+  CU(cudaEventRecord(c->ev_t0, c->s_comp));
+  for (int i = 0; i < reps; ++i) {
+    CU(launch_pass(c, T, cur, cur ^ 1, g.Z0, g.Z0 + g.nz));
+    cur ^= 1;
+  }
+  CU(cudaEventRecord(c->ev_t1, c->s_comp));
+  CU(cudaStreamSynchronize(c->s_comp));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+  *ms_per_pass = (double)ms / reps;
+  c->tfuse_used = T;
+  return GIRIH_OK;
+}
+
+extern "C" int girih_gpu_last_elapsed_ms(girih_gpu_ctx *c, double *compute_ms, double *comm_ms, double *total_ms) {
+  if (!c) return GIRIH_ERR_ARG;
+  if (compute_ms) *compute_ms = c->ms_compute;
+  if (comm_ms) *comm_ms = c->ms_comm;
+  if (total_ms) *total_ms = c->ms_total;
+  return GIRIH_OK;
+}
+extern "C" int girih_gpu_last_launch_info(girih_gpu_ctx *c, int *n_kernels, int *n_passes, int *n_steps, int *tfuse_used) {
+  if (!c) return GIRIH_ERR_ARG;
+  if (n_kernels) *n_kernels = c->n_kernels;
+  if (n_passes) *n_passes = c->n_passes;
+  if (n_steps) *n_steps = c->n_steps;
+  if (tfuse_used) *tfuse_used = c->tfuse_used;
+  return GIRIH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NaN / zero scan of U1 (src/utils.c:819-840)
+// ------------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void k_scan(DevGrid g, const R *__restrict__ u, int hx, int hy, int hz, unsigned long long *out) {
+  // over the cells of the HOST array extent: (hx, hy, hz) starting at (X0-r, Y0-r, Z0-r)
+  unsigned long long nans = 0, zeros = 0;
+  const long long n = (long long)hx * hy * hz;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % hx);
+    const long long t = i / hx;
+    const int y = (int)(t % hy), z = (int)(t / hy);
+    const R v = u[((long long)(z + g.Z0 - g.r) * g.ny_dev + (y + g.Y0 - g.r)) * g.px + (x + g.X0 - g.r)];
+    nans += (v * (R)0 != (R)0) ? 1 : 0;
+    zeros += (fabs((double)v) < 1e-6) ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    nans += __shfl_down_sync(0xffffffffu, nans, o);
+    zeros += __shfl_down_sync(0xffffffffu, zeros, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (nans) atomicAdd(out, nans);
+    if (zeros) atomicAdd(out + 1, zeros);
+  }
+}
+
+extern "C" int girih_gpu_scan_u1(girih_gpu_ctx *c, uint64_t *n_nan_inf, uint64_t *n_zero) {
+  if (!c) return GIRIH_ERR_ARG;
+  if (!c->uploaded) return fail(c, GIRIH_ERR_STATE, "scan before upload");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemsetAsync(c->d_scan, 0, 2 * sizeof(unsigned long long), c->s_comp));
+  // the reference scans all ln_domain cells including the x padding, which is zero; count the
+  // padding cells as zeros to report the same percentage
+  const int hx = c->g.nx + 2 * c->g.r;
+  if (c->es == 8) k_scan<double><<<148 * 8, 256, 0, c->s_comp>>>(c->g, (const double *)c->dU[0], hx, c->hshape[1], c->hshape[2], c->d_scan);
+  else            k_scan<float><<<148 * 8, 256, 0, c->s_comp>>>(c->g, (const float *)c->dU[0], hx, c->hshape[1], c->hshape[2], c->d_scan);
+  CU(cudaGetLastError());
+  unsigned long long h[2];
+  CU(cudaMemcpyAsync(h, c->d_scan, sizeof(h), cudaMemcpyDeviceToHost, c->s_comp));
+  CU(cudaStreamSynchronize(c->s_comp));
+  const unsigned long long pad = (unsigned long long)(c->hshape[0] - hx) * c->hshape[1] * c->hshape[2];
+  if (n_nan_inf) *n_nan_inf = h[0];
+  if (n_zero) *n_zero = h[1] + pad;
+  return GIRIH_OK;
+}

@@ -1,0 +1,256 @@
+// kernels_r1.cuh -- z-streamed, temporally fused sweep for the radius-1 star operators
+// (table slots 1, 2, 3, 5).  T = 1 is the single-step stepper (ts 0/1), T > 1 the GPU form of
+// GIRIH's wavefront-diamond sweep (ts 2; src/kernels/stencils_1wf.ic:33-82 and
+// src/kernels/diamond_ts.c:427-488 describe the CPU schedule this replaces).
+//
+// Schedule (one CTA = NW warps):
+//   * a lane owns VX = 16 B / sizeof(Real) consecutive x points, so every global access is a
+//     coalesced 128-bit load/store; a warp spans WX = 32*VX points of one row
+//   * a thread owns PY consecutive rows -> register tile VX x PY; the CTA tile is WX x (NW*PY)
+//   * the CTA streams along z.  For every fused level l < T each thread keeps its own points of
+//     the two newest planes of that level in registers (B = z-2, C = z-1 relative to the plane F
+//     that level l produces in this iteration): the z neighbours never touch shared memory
+//   * x neighbours inside a lane come from registers, across lanes from warp shuffles
+//   * y neighbours inside a thread come from registers; only the first/last row of each warp's
+//     strip goes through shared memory (double buffered, ONE __syncthreads per z iteration for
+//     all T levels)
+//   * level l+1 lags level l by one plane (the reference's `kt -= NHALO` skew,
+//     stencils_1wf.ic:77), so T time steps cost one read and one write of the grid
+//   * tiles overlap by HX >= T columns and T rows per side (halo depth = steps x radius);
+//     whatever a tile computes outside its core is discarded.  Points that are not interior
+//     points of the GLOBAL domain pass their value through every level, which keeps the
+//     Dirichlet frame (and the +100.1 source planes, src/utils.c:679-696) exactly as the
+//     reference, which simply never writes them (xb = r .. xe = nx + r).
+#pragma once
+#include "common.cuh"
+#include "stencil_expr.cuh"
+
+namespace girih {
+
+template <typename R> struct R1Args {
+  DevGrid g;
+  const R *__restrict__ in;     // level L   (read)
+  R *__restrict__ out;          // level L+T (written, interior of this slab only)
+  const R *__restrict__ coef;   // per-point coefficient arrays (slots 2,3,5) or nullptr
+  long long coef_stride;
+  ConstCoef<R> cc;              // scalar coefficients (slot 1)
+  int zb0, ze0;                 // output planes [zb0, ze0) of this launch (device z)
+  int zchunk;                   // output planes per CTA
+};
+
+template <typename R, int T, int PY, int NW> struct R1Cfg {
+  static constexpr int VX = Vec<R>::N;
+  static constexpr int WX = 32 * VX;
+  static constexpr int HX = ((T + VX - 1) / VX) * VX;   // x overlap, kept 16-byte aligned
+  static constexpr int UX = WX - 2 * HX;                // core columns per tile
+  static constexpr int H = NW * PY;
+  static constexpr int UY = H - 2 * T;                  // core rows per tile
+  static constexpr int PF = (T == 1) ? 2 : 1;           // planes prefetched ahead
+  static constexpr int MINB = (T == 1 && NW <= 8) ? 2 : 1;   // resident CTAs per SM aimed for
+  static constexpr size_t SMEM = (size_t)T * 2 * NW * 2 * WX * sizeof(R);
+  static_assert(UY > 0 && UX > 0, "tile too small for this fusion depth");
+};
+
+// neighbour accessor over registers: centre plane C, plane below B, plane above F
+template <typename R> struct RegNb1 {
+  R c, xm, xp, ym, yp, zm, zp;
+  template <int DX, int DY, int DZ> __device__ __forceinline__ R at() const {
+    if constexpr (DX == 0 && DY == 0 && DZ == 0) return c;
+    else if constexpr (DX == -1) return xm;
+    else if constexpr (DX == 1) return xp;
+    else if constexpr (DY == -1) return ym;
+    else if constexpr (DY == 1) return yp;
+    else if constexpr (DZ == -1) return zm;
+    else return zp;
+  }
+};
+
+template <int K, typename R, int T, int PY, int NW>
+__global__ void __launch_bounds__(32 * NW, R1Cfg<R, T, PY, NW>::MINB)
+k_r1(const R1Args<R> a) {
+  using Cfg = R1Cfg<R, T, PY, NW>;
+  constexpr int VX = Cfg::VX, WX = Cfg::WX, HX = Cfg::HX, UX = Cfg::UX, H = Cfg::H, UY = Cfg::UY;
+  constexpr int PF = Cfg::PF;
+  constexpr int NCA = KTraits<K>::NCA;
+  static_assert(KTraits<K>::R == 1 && KTraits<K>::TO == 1, "radius-1, first-order-in-time only");
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // edge[l][parity][warp][0 = first row, 1 = last row][WX]
+  R *edge = reinterpret_cast<R *>(smem_raw);
+  auto edge_ptr = [&](int l, int par, int w, int which) -> R * {
+    return edge + ((((size_t)l * 2 + par) * NW + w) * 2 + which) * WX;
+  };
+
+  const DevGrid &g = a.g;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = g.X0 - HX + (int)blockIdx.x * UX + lane * VX;   // my first column (device x)
+  const int y0 = g.Y0 - T + (int)blockIdx.y * UY + warp * PY;   // my first row
+  const int zb = a.zb0 + (int)blockIdx.z * a.zchunk;
+  const int ze = min(zb + a.zchunk, a.ze0);
+
+  // per-point facts that do not change along z
+  const bool x_alloc = (x >= 0) && (x + VX <= g.px);
+  bool row_alloc[PY];
+  unsigned interior_xy = 0;   // bit j*VX+e: point is an interior point in x and y
+  unsigned core_xy = 0;       // ... and lies in this tile's core -> this tile stores it
+#pragma unroll
+  for (int j = 0; j < PY; ++j) {
+    const int y = y0 + j;
+    row_alloc[j] = x_alloc && (y >= 0) && (y < g.ny_dev);
+    const bool yin = (y >= g.Y0) && (y < g.Y0 + g.ny);
+    const int ly = warp * PY + j;
+    const bool ycore = (ly >= T) && (ly < H - T);
+#pragma unroll
+    for (int e = 0; e < VX; ++e) {
+      const bool xin = (x + e >= g.X0) && (x + e < g.X0 + g.nx);
+      const int lx = lane * VX + e;
+      const bool xcore = (lx >= HX) && (lx < WX - HX);
+      if (xin && yin) interior_xy |= 1u << (j * VX + e);
+      if (xin && yin && xcore && ycore) core_xy |= 1u << (j * VX + e);
+    }
+  }
+  const long long row0 = (long long)y0 * g.px + x;   // offset of my first point inside a plane
+
+  R B[T][PY][VX], C[T][PY][VX];
+#pragma unroll
+  for (int l = 0; l < T; ++l)
+#pragma unroll
+    for (int j = 0; j < PY; ++j)
+#pragma unroll
+      for (int e = 0; e < VX; ++e) { B[l][j][e] = (R)0; C[l][j][e] = (R)0; }
+
+  auto load_plane = [&](int z, R (&dst)[PY][VX]) {
+    const bool zok = (z >= 0) && (z < g.nz_dev);
+    const R *p = a.in + (long long)z * g.pxy + row0;
+#pragma unroll
+    for (int j = 0; j < PY; ++j) {
+      if (zok && row_alloc[j]) ld128<R>(p + (long long)j * g.px, dst[j]);
+      else {
+#pragma unroll
+        for (int e = 0; e < VX; ++e) dst[j][e] = (R)0;
+      }
+    }
+  };
+
+  R nxt[PF][PY][VX];
+#pragma unroll
+  for (int q = 0; q < PF; ++q) load_plane(zb - T + q, nxt[q]);
+
+  const int nit = (ze - zb) + 2 * T;
+  for (int it = 0; it < nit; ++it) {
+    const int zin = zb - T + it;
+    const int cur = it & 1;
+
+    R F[PY][VX];
+#pragma unroll
+    for (int j = 0; j < PY; ++j)
+#pragma unroll
+      for (int e = 0; e < VX; ++e) F[j][e] = nxt[0][j][e];
+#pragma unroll
+    for (int q = 0; q + 1 < PF; ++q)
+#pragma unroll
+      for (int j = 0; j < PY; ++j)
+#pragma unroll
+        for (int e = 0; e < VX; ++e) nxt[q][j][e] = nxt[q + 1][j][e];
+    if (it + PF < nit) load_plane(zin + PF, nxt[PF - 1]);
+
+    // publish the first/last row of the level-0 plane for next iteration's level-1 update
+    st128<R>(edge_ptr(0, cur, warp, 0) + lane * VX, F[0]);
+    st128<R>(edge_ptr(0, cur, warp, 1) + lane * VX, F[PY - 1]);
+
+#pragma unroll
+    for (int l = 0; l < T; ++l) {
+      // level l+1 at plane zc from level l planes zc-1 (B), zc (C), zc+1 (F)
+      const int zc = zin - l - 1;
+      const bool z_interior = (zc >= g.zlo) && (zc < g.zhi);
+
+      // rows just outside my strip, owned by the neighbouring warps (written last iteration)
+      R up[VX], dn[VX];
+      {
+        const int wu = (warp > 0) ? warp - 1 : 0, wd = (warp < NW - 1) ? warp + 1 : NW - 1;
+        ld128s(edge_ptr(l, cur ^ 1, wu, 1) + lane * VX, up);
+        ld128s(edge_ptr(l, cur ^ 1, wd, 0) + lane * VX, dn);
+      }
+
+      // per-point coefficients of plane zc (slots 2, 3, 5)
+      R cf[NCA > 0 ? NCA : 1][PY][VX];
+      if constexpr (NCA > 0) {
+        const bool zok = (zc >= 0) && (zc < g.nz_dev);
+        const R *cp = a.coef + (long long)zc * g.pxy + row0;
+#pragma unroll
+        for (int m = 0; m < NCA; ++m)
+#pragma unroll
+          for (int j = 0; j < PY; ++j) {
+            if (zok && row_alloc[j]) ld128<R>(cp + (long long)m * a.coef_stride + (long long)j * g.px, cf[m][j]);
+            else {
+#pragma unroll
+              for (int e = 0; e < VX; ++e) cf[m][j][e] = (R)0;
+            }
+          }
+      }
+
+      R O[PY][VX];
+#pragma unroll
+      for (int j = 0; j < PY; ++j) {
+        const R left = __shfl_up_sync(0xffffffffu, C[l][j][VX - 1], 1);
+        const R right = __shfl_down_sync(0xffffffffu, C[l][j][0], 1);
+#pragma unroll
+        for (int e = 0; e < VX; ++e) {
+          RegNb1<R> n;
+          n.c = C[l][j][e];
+          n.xm = (e > 0) ? C[l][j][e > 0 ? e - 1 : 0] : left;
+          n.xp = (e < VX - 1) ? C[l][j][e < VX - 1 ? e + 1 : 0] : right;
+          n.ym = (j > 0) ? C[l][j > 0 ? j - 1 : 0][e] : up[e];
+          n.yp = (j < PY - 1) ? C[l][j < PY - 1 ? j + 1 : 0][e] : dn[e];
+          n.zm = B[l][j][e];
+          n.zp = F[j][e];
+          R val;
+          if constexpr (NCA > 0) {
+            RegCoef<R, NCA> rc;
+#pragma unroll
+            for (int m = 0; m < NCA; ++m) rc.v[m] = cf[m][j][e];
+            val = StencilExpr<K>::template eval<R>(n, rc, (R)0, (R)0);
+          } else {
+            val = StencilExpr<K>::template eval<R>(n, a.cc, (R)0, (R)0);
+          }
+          const bool upd = z_interior && ((interior_xy >> (j * VX + e)) & 1u);
+          O[j][e] = upd ? val : n.c;
+        }
+      }
+
+      // rotate this level's z window and hand the new plane to the next level
+#pragma unroll
+      for (int j = 0; j < PY; ++j)
+#pragma unroll
+        for (int e = 0; e < VX; ++e) {
+          B[l][j][e] = C[l][j][e];
+          C[l][j][e] = F[j][e];
+          F[j][e] = O[j][e];
+        }
+      if (l + 1 < T) {
+        st128<R>(edge_ptr(l + 1, cur, warp, 0) + lane * VX, F[0]);
+        st128<R>(edge_ptr(l + 1, cur, warp, 1) + lane * VX, F[PY - 1]);
+      }
+    }
+
+    // F is level T at plane zin - T
+    const int zo = zin - T;
+    if (zo >= zb && zo < ze) {
+      R *q = a.out + (long long)zo * g.pxy + row0;
+#pragma unroll
+      for (int j = 0; j < PY; ++j) {
+        const unsigned m = (core_xy >> (j * VX)) & ((1u << VX) - 1u);
+        if (m == (1u << VX) - 1u) {
+          st128<R>(q + (long long)j * g.px, F[j]);
+        } else if (m != 0u) {
+#pragma unroll
+          for (int e = 0; e < VX; ++e)
+            if ((m >> e) & 1u) q[(long long)j * g.px + e] = F[j][e];
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace girih

@@ -1,0 +1,183 @@
+/*
+ * perf.c -- the performance harness: src/performance.c:29-127 (performance_test) and the report of
+ * src/utils.c:808-982 (performance_results).  Differences that come with the device:
+ *   - the per-test time is the cudaEvent interval of the stepper (max over ranks), not MPI_Wtime
+ *   - the NaN / zero scan of the final U1 (src/utils.c:819-840) runs on the device
+ *   - extra "GPU ..." lines report what GIRIH's keys cannot: the steps really executed, the true
+ *     LUP/s, achieved HBM GB/s per pass and the roofline fraction
+ * Every "Key: value" line of the reference is printed with the same spelling, including the
+ * GStencil/s quirk (MEDIAN multiplies by nt, MIN/MAX use the per-step time, src/utils.c:872-875).
+ */
+#define _POSIX_C_SOURCE 200112L
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "girih_host.h"
+
+static int cmp_double(const void *a, const void *b) {
+  const double x = *(const double *)a, y = *(const double *)b;
+  return (x > y) - (x < y);
+}
+
+static double hbm_peak_gbs(void) {
+  /* measured copy bandwidth of this pool's B200 (MEASURED_PEAKS.json); override with GIRIH_HBM_GBS */
+  const char *e = getenv("GIRIH_HBM_GBS");
+  return e ? atof(e) : 6538.9;
+}
+
+static void performance_results(Parameters *p, double t, double t_max, double t_min, double t_med,
+                                double t_main_max, double t_main_min) {
+  double in[5], mx[5], mn[5], sm[5];
+  uint64_t nans = 0, zeros = 0, zeroes_p;
+  girih_kernel_desc kd;
+  int rc;
+
+  rc = girih_gpu_scan_u1(p->gpu, &nans, &zeros);
+  if (rc != GIRIH_OK) girih_fatal(NULL, "girih_gpu_scan_u1: %s", girih_gpu_strerror(rc));
+  zeroes_p = 100 * zeros / p->ln_domain;
+  if (zeroes_p > 90) {
+    printf("\n******************************************************\n");
+    printf("##WARNING[rank:%d]: %llu%% of the sub domain contains zeroes. This might result in inaccurate performance results\n",
+           p->mpi_rank, (unsigned long long)zeroes_p);
+    printf("******************************************************\n\n");
+  }
+  if (nans > 0) {
+    printf("\n******************************************************\n");
+    printf("##WARNING[rank:%d]: %llu nan and/or -inf/inf values in the final sub domain solution. This might result in inaccurate performance results\n",
+           p->mpi_rank, (unsigned long long)nans);
+    printf("******************************************************\n\n");
+  }
+
+  in[0] = p->prof.compute; in[1] = p->prof.communicate; in[2] = p->prof.wait; in[3] = p->prof.others; in[4] = p->prof.total;
+  team_reduce(in, mx, mn, sm, 5, p->mpi_rank);
+  if (p->mpi_rank != 0) return;
+  girih_kernel_info(p->target_kernel, &kd);
+
+  printf("Total memory allocation per MPI rank: %llu MiB\n", (unsigned long long)(sizeof(real_t) * p->ln_domain * 3 / 1024 / 1024));
+  printf("Total time(s): %e\n", t * p->n_tests);
+  printf("time/test(s): %e\n", t);
+  if (p->target_ts != 2) {
+    printf("\nRANK0 GStencil/s MEDIAN: %f  \n", p->ln_stencils / (1e9 * t_med) * p->nt);
+    printf("RANK0 GStencil/s    MIN: %f  \n", p->ln_stencils / (1e9 * t_max));
+    printf("RANK0 GStencil/s    AVG: %f  \n", p->ln_stencils / (1e9 * (t / p->nt)));
+    printf("RANK0 GStencil/s    MAX: %f  \n", p->ln_stencils / (1e9 * t_min));
+    printf("\n******************************************************\n");
+    printf("RANK0 Total: %f (s) -%06.2f%%\n", p->prof.total, 100.0);
+    printf("RANK0 Computation: %f (s) - %05.2f%%\n", p->prof.compute, p->prof.compute / p->prof.total * 100);
+    printf("RANK0 Communication: %f (s) - %05.2f%%\n", p->prof.communicate, p->prof.communicate / p->prof.total * 100);
+    printf("RANK0 Waiting: %f (s) - %05.2f%%\n", p->prof.wait, p->prof.wait / p->prof.total * 100);
+    printf("RANK0 Other: %f (s) - %05.2f%%\n", p->prof.others, p->prof.others / p->prof.total * 100);
+    printf("\n******************************************************\n");
+    printf("MEAN Total: %f (s) -%06.2f%%\n", sm[4] / p->mpi_size, 100.0);
+    printf("MEAN Computation: %f (s) - %05.2f%%\n", sm[0] / p->mpi_size, sm[0] / sm[4] * 100);
+    printf("MEAN Communication: %f (s) - %05.2f%%\n", sm[1] / p->mpi_size, sm[1] / sm[4] * 100);
+    printf("MEAN Waiting: %f (s) - %05.2f%%\n", sm[2] / p->mpi_size, sm[2] / sm[4] * 100);
+    printf("MEAN Other: %f (s) - %05.2f%%\n", sm[3] / p->mpi_size, sm[3] / sm[4] * 100);
+    printf("\n******************************************************\n");
+    printf("MAX Total: %f (s)\n", mx[4]);
+    printf("MAX Computation: %f (s)\n", mx[0]);
+    printf("MAX Communication: %f (s)\n", mx[1]);
+    printf("MAX Waiting: %f (s)\n", mx[2]);
+    printf("MAX Other: %f (s)\n", mx[3]);
+    printf("\n******************************************************\n");
+    printf("MIN Total: %f (s)\n", mn[4]);
+    printf("MIN Computation: %f (s)\n", mn[0]);
+    printf("MIN Communication: %f (s)\n", mn[1]);
+    printf("MIN Waiting: %f (s)\n", mn[2]);
+    printf("MIN Other: %f (s)\n", mn[3]);
+  } else {
+    const double total_stencils = ((double)p->ln_stencils * (double)p->nt - (double)p->idiamond_pro_epi_logue_updates) / 1e6;
+    printf("\nTotal RANK0 MStencil/s MIN: %f  \n", p->ln_stencils / (1e6 * t_max));
+    printf("Total RANK0 MStencil/s MAX: %f  \n", p->ln_stencils / (1e6 * t_min));
+    printf("******************************************************\n");
+    printf("MWD main-loop RANK0 MStencil/s MIN: %f\n", total_stencils / t_main_max);
+    printf("MWD main-loop RANK0 MStencil/s MAX: %f\n", total_stencils / t_main_min);
+    printf("******************************************************\n");
+    printf("%-27s %f (s) - %05.2f%%\n", "RANK0 ts main loop:", p->prof.ts_main, p->prof.ts_main / p->prof.total * 100);
+    printf("%-27s %f (s) - %05.2f%%\n", "RANK0 ts prologue/epilogue:", p->prof.ts_others, p->prof.ts_others / p->prof.total * 100);
+    printf("%-27s %f (s) - %05.2f%%\n", "RANK0 ts others:", p->prof.total - (p->prof.ts_main + p->prof.ts_others),
+           (p->prof.total - (p->prof.ts_main + p->prof.ts_others)) / p->prof.total * 100);
+  }
+  printf("\n******************************************************\n");
+  {
+    /* best test: t_min is the per-"cycle" time of the reference (test time / nt) */
+    const double best_test = t_min * p->nt;
+    const double steps = (double)p->steps_executed;
+    const double glups = (double)p->n_stencils * steps / best_test / 1e9;
+    const int passes_T = p->tfuse_used > 0 ? p->tfuse_used : 1;
+    const double bytes_per_lup = (double)kd.words_per_lup * sizeof(real_t);
+    const double gbs_step = glups * bytes_per_lup;                 /* if every step were an HBM pass */
+    printf("GPU count: %d\n", p->mpi_size);
+    printf("GPU steps executed per test: %d\n", p->steps_executed);
+    printf("GPU fused steps per pass (T): %d\n", passes_T);
+    printf("GPU true GLUP/s (all GPUs): %f\n", glups);
+    printf("GPU algorithmic bytes per LUP (single step): %.0f\n", bytes_per_lup);
+    printf("GPU effective HBM GB/s at single-step balance: %f\n", gbs_step);
+    printf("GPU single-step roofline GLUP/s (%.1f GB/s measured peak x %d GPUs): %f\n", hbm_peak_gbs(), p->mpi_size,
+           hbm_peak_gbs() * p->mpi_size / bytes_per_lup);
+    printf("GPU GLUP/s over single-step roofline: %f\n", glups / (hbm_peak_gbs() * p->mpi_size / bytes_per_lup));
+    printf("******************************************************\n");
+  }
+}
+
+void performance_test(Parameters *p) {
+  int i, tests_remain;
+  double t = 0.0, t_min = 1000000.0, t_max = -1.0, t_med, tpercycle, tpertest;
+  double t_main_max = -1.0, t_main_min = 1000000.0;
+  double *ttests = (double *)malloc((size_t)p->n_tests * sizeof(double));
+  time_t now;
+
+  if (p->mpi_rank == 0) {
+    time(&now);
+    printf("Started on %s", ctime(&now));
+    if (p->verbose == 1) print_param(p);
+  }
+  arrays_allocate(p);
+  init_coeff(p);
+  domain_data_fill(p);
+  gpu_attach(p);
+
+  if (p->mpi_rank == 0) {
+    printf("\n******************************************************\n");
+    printf("Performance results\n");
+    printf("******************************************************\n");
+  }
+  tests_remain = p->n_tests;
+  while (tests_remain--) {
+    double mine, mx;
+    reset_timers(&p->prof);
+    team_barrier();
+    TSList[p->target_ts].func(p);
+    team_barrier();
+    mine = p->prof.total;
+    team_reduce(&mine, &mx, NULL, NULL, 1, p->mpi_rank);   /* device time, max over ranks */
+    tpertest = mx;
+    tpercycle = tpertest / p->nt;
+    ttests[tests_remain] = tpertest;
+    p->prof.wait += (mx - mine);
+    p->prof.communicate += p->prof.wait;
+    p->prof.total = mx;
+    p->prof.others = p->prof.total - p->prof.communicate - p->prof.compute;
+    if (p->mpi_rank == 0) {
+      printf("Rank 0 TEST#%02d time: %e\n", (p->n_tests - tests_remain), tpertest);
+      if (tests_remain == 0) printf("******************************************************\n");
+    }
+    t += tpertest / p->n_tests;
+    if (t_min > tpercycle) t_min = tpercycle;
+    if (t_max < tpercycle) t_max = tpercycle;
+    if (t_main_min > p->prof.ts_main) t_main_min = p->prof.ts_main;
+    if (t_main_max < p->prof.ts_main) t_main_max = p->prof.ts_main;
+  }
+  qsort(ttests, (size_t)p->n_tests, sizeof(double), cmp_double);
+  t_med = ttests[p->n_tests / 2];
+  (void)i;
+  performance_results(p, t, t_max, t_min, t_med, t_main_max, t_main_min);
+  if (p->mpi_rank == 0) {
+    time(&now);
+    printf("COMPLETED SUCCESSFULLY on %s", ctime(&now));
+  }
+  gpu_detach(p);
+  arrays_free(p);
+  free(ttests);
+}

@@ -1,0 +1,176 @@
+/*
+ * girih_cuda.h -- C ABI of the B200 (sm_100a) implementation of GIRIH's star-stencil time
+ * stepper.  Plain C: pointers, ints and sizes only; nothing here throws, exits or prints.
+ *
+ * What it replaces in the reference (paths relative to the GIRIH source tree):
+ *   - the operator plugin point  spt_blk_func_t / mwd_func_t   src/data_structures.h:202-209,
+ *     tables src/kernels/stencils.c:260-352, selected by set_kernels() src/utils.c:253-300
+ *   - the time-stepper plugin point  struct time_stepper {name, void (*func)(Parameters*)}
+ *     src/data_structures.h:294-297, table TSList[] src/wrappers.h:29-37, called from
+ *     src/performance.c:75 and src/verification.c:37
+ *   - the halo exchange of src/mpi_utils.c:116-202 + src/kernels/nb_naive_ts.c:32-155
+ *     (z-slab decomposition only, NCCL send/recv instead of MPI)
+ * The C host (girih_b200/host/, the `mwd_kernel` executable) registers three steppers in its own
+ * TSList[] that call girih_gpu_run_single / girih_gpu_run_fused below; INTEGRATION.md shows the
+ * stub a GIRIH maintainer would add to the original tree.
+ *
+ * Ownership: the caller owns the host arrays (Parameters.U1/U2/U3/coef, allocated by
+ * arrays_allocate(), src/utils.c:153-218) before and after every call; the context owns all
+ * device memory.  After a stepper returns, the reference reads p->U1 (src/verification.c:974,
+ * src/utils.c:820-828): call girih_gpu_download() for that.
+ *
+ * Error convention: every function returns 0 (GIRIH_OK) or a positive girih_status; the C host
+ * turns non-zero into the reference's "ERROR: ..." + exit(1) (src/data_structures.h:299-314).
+ * There is NO CPU fallback: without a CUDA device girih_gpu_create() fails with
+ * GIRIH_ERR_NO_DEVICE.
+ *
+ * Threading: a context is bound to one CUDA device and must be driven by one host thread at a
+ * time.  Multi-GPU = one context per GPU (one process per GPU under torchrun, or one host thread
+ * per GPU inside mwd_kernel --npz N), joined by girih_gpu_comm_init().
+ */
+#ifndef GIRIH_CUDA_H_
+#define GIRIH_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct girih_gpu_ctx girih_gpu_ctx;
+
+enum girih_status {
+  GIRIH_OK = 0,
+  GIRIH_ERR_ARG = 1,          /* bad argument / shape                                   */
+  GIRIH_ERR_NO_DEVICE = 2,    /* no CUDA device or driver: there is no CPU fallback     */
+  GIRIH_ERR_CUDA = 3,         /* a CUDA runtime call failed (see girih_gpu_last_error)  */
+  GIRIH_ERR_UNSUPPORTED = 4,  /* table slot without a GPU operator (solar, kernel 6)    */
+  GIRIH_ERR_NCCL = 5,         /* NCCL missing or a NCCL call failed                     */
+  GIRIH_ERR_STATE = 6,        /* call order (e.g. run before upload)                    */
+  GIRIH_ERR_FRAME = 7         /* fused stepping needs identical Dirichlet frames in U1/U2 */
+};
+
+/* Stencil_Shapes / Stencil_Coefficients, src/data_structures.h:114-126 (same numbering). */
+enum girih_shape { GIRIH_STAR = 0, GIRIH_TTI = 1, GIRIH_BOX = 2 };
+enum girih_coeff {
+  GIRIH_COEF_CONSTANT = 0, GIRIH_COEF_VARIABLE = 1, GIRIH_COEF_VARIABLE_AXSYM = 2,
+  GIRIH_COEF_VARIABLE_NOSYM = 3, GIRIH_COEF_SOLAR = 4
+};
+
+/* One row of the operator table: struct StencilInfo, src/data_structures.h:225-233, plus the
+ * bookkeeping the GPU side adds. */
+typedef struct {
+  const char *name;      /* "star" / "box"                                              */
+  int r;                 /* semi-bandwidth                                              */
+  int time_order;        /* 1 or 2                                                      */
+  int nd;                /* domain-sized arrays streamed per step (reference's count)   */
+  int shape;             /* enum girih_shape                                            */
+  int coeff;             /* enum girih_coeff                                            */
+  int n_coef_arrays;     /* domain-sized coefficient arrays (0 for constant)            */
+  int n_coef_scalars;    /* scalar coefficients read from coef[] (constant kernels)     */
+  int words_per_lup;     /* algorithmic words moved per lattice update      */
+  int max_tfuse;         /* deepest temporal fusion the GPU stepper offers (>=1)        */
+  int gpu_supported;     /* 0 for the solar slot (src/kernels/stencils.h:40-47 analogue) */
+} girih_kernel_desc;
+
+/* stencil_info_list[] of src/kernels/stencils.c:260-271: indices 0..7 as printed by --list. */
+int girih_kernel_count(void);
+int girih_kernel_info(int target_kernel, girih_kernel_desc *out);
+
+/* Number of visible CUDA devices (0 and GIRIH_ERR_NO_DEVICE when there is none). */
+int girih_gpu_count(int *n);
+
+/*
+ * Create the device-side state of ONE z-slab.
+ *   device          CUDA ordinal
+ *   target_kernel   operator table index (--target-kernel)
+ *   elem_size       4 (float build) or 8 (-DDP=1 build), src/data_structures.h:90-105
+ *   stencil_shape   LOCAL interior nx,ny,nz of this slab (Parameters.lstencil_shape)
+ *   domain_shape    LOCAL host array shape nnx,nny,nnz = interior + 2r (+ x padding), x fastest
+ *                   (Parameters.ldomain_shape, src/utils.c:367-374); z halo planes between slabs
+ *                   are r deep on the host side exactly as in src/mpi_utils.c:173-200
+ *   rank, nranks    position in the 1-D z chain (--npz); rank 0 holds the lowest z
+ */
+int girih_gpu_create(girih_gpu_ctx **ctx, int device, int target_kernel, int elem_size,
+                     const int stencil_shape[3], const int domain_shape[3], int rank, int nranks);
+void girih_gpu_destroy(girih_gpu_ctx *ctx);
+
+/* Communicator bootstrap for nranks > 1 (replaces mpi_topology_init, src/mpi_utils.c:63-113):
+ * rank 0 calls girih_gpu_comm_unique_id(), the host distributes the 128 bytes by its own means
+ * (torch.distributed broadcast, a shared variable between threads, ...), every rank calls
+ * girih_gpu_comm_init().  NCCL is loaded at run time (libnccl.so.2). */
+#define GIRIH_COMM_ID_BYTES 128
+int girih_gpu_comm_unique_id(void *id, size_t len);
+int girih_gpu_comm_init(girih_gpu_ctx *ctx, const void *id, size_t len);
+
+/* Host -> device of the arrays arrays_allocate()/init_coeff()/domain_data_fill() produced
+ * (src/performance.c:50-52).  U3 (roc2) may be NULL unless time_order == 2; coef holds
+ * n_coef_scalars values (constant) or n_coef_arrays*ln_domain values (variable), in the
+ * reference's layout COEF(m,i,j,k) = coef[idx + ln_domain*m], src/kernels/stencils.h:32.
+ * Outside the timed region, like the reference's allocation/fill. */
+int girih_gpu_upload(girih_gpu_ctx *ctx, const void *U1, const void *U2, const void *U3,
+                     const void *coef);
+/* Device -> host of U1 and/or U2 (either may be NULL) into arrays of domain_shape. */
+int girih_gpu_download(girih_gpu_ctx *ctx, void *U1, void *U2);
+/* Same transfers from/to page-locked host memory, asynchronous on the context's stream and
+ * followed by a stream synchronise -- used for end-to-end timing. */
+int girih_gpu_upload_fields(girih_gpu_ctx *ctx, const void *U1, const void *U2);
+
+/*
+ * Time steppers.  All follow the reference's parity convention: global step s = 1,2,... reads
+ * the array written by step s-1 and writes U1 when s is odd, U2 when s is even
+ * (src/kernels/nb_naive_ts.c:187-203, src/kernels/diamond_ts.c:440-444).  After `nsteps` steps
+ * the newest level is in U1 (nsteps odd) or U2 (even) and the other array holds level nsteps-1,
+ * bit-identical to the reference steppers.
+ *
+ * girih_gpu_run_single: ts 0 "Spatial Blocking" (overlap = 0) and ts 1 "Halo-first"
+ *   (overlap = 1: boundary slabs first, halo exchange overlapped with the interior;
+ *   src/kernels/halo_first_ts.c:156-194).  One HBM pass per step.
+ * girih_gpu_run_fused: ts 2 "Diamond": the GPU analogue of the MWD sweep
+ *   (src/kernels/diamond_ts.c:871-976, stencils_1wf.ic:33-82): tfuse time steps are fused per
+ *   HBM pass with a z-streaming wavefront; halo depth between slabs = tfuse * r.
+ *   tfuse <= 0 selects the default for the operator; tfuse is clamped to max_tfuse.
+ * The GIRIH CLI passes nsteps = nt rounded up to even (ts 0/1) or nt-1 after the diamond
+ * rounding of nt (ts 2, src/kernels/diamond_utils.c:1042-1056).
+ */
+int girih_gpu_run_single(girih_gpu_ctx *ctx, int nsteps, int overlap);
+int girih_gpu_run_fused(girih_gpu_ctx *ctx, int nsteps, int tfuse);
+
+/* One application of the operator over the box [xb,xe) x [yb,ye) x [zb,ze) in HOST index space
+ * (the spt_blk_func_t contract, src/kernels/stencils_spt_blk.ic:19-48): dst=1 writes U1 from U2,
+ * dst=2 writes U2 from U1. */
+int girih_gpu_step_box(girih_gpu_ctx *ctx, int dst, int xb, int yb, int zb, int xe, int ye, int ze);
+
+/* cudaEvent timing of the last run_* call, in milliseconds (replaces the MPI_Wtime brackets of
+ * src/performance.c:70-78 and the Profile fields of src/data_structures.h:141-143).
+ * compute = kernel time on the compute stream, comm = halo exchange on the comm stream,
+ * total = first launch to last completion. */
+int girih_gpu_last_elapsed_ms(girih_gpu_ctx *ctx, double *compute_ms, double *comm_ms,
+                              double *total_ms);
+/* Launch accounting of the last run_* call: kernels launched, fused passes, steps executed. */
+int girih_gpu_last_launch_info(girih_gpu_ctx *ctx, int *n_kernels, int *n_passes, int *n_steps,
+                               int *tfuse_used);
+
+/* Measurement hook for the roofline figure: launches `reps` passes of `tfuse` fused steps back to
+ * back over the whole slab (ping-ponging U1/U2, so the fields keep evolving) and returns the
+ * average device time of ONE pass = one kernel launch, from cudaEvents on the launching stream.
+ * No halo exchange: single-slab contexts only. */
+int girih_gpu_time_pass(girih_gpu_ctx *ctx, int tfuse, int reps, double *ms_per_pass);
+
+/* NaN/Inf and near-zero scan of the final U1 over the whole local domain
+ * (src/utils.c:819-840), done on the device. */
+int girih_gpu_scan_u1(girih_gpu_ctx *ctx, uint64_t *n_nan_inf, uint64_t *n_zero);
+
+/* Tuning knobs (all optional).  Keys: "variant" (0 auto, 1 naive, 2 streamed),
+ * "zchunk" (output planes per CTA), "tile" (encoded PY*100+NW). */
+int girih_gpu_set_option(girih_gpu_ctx *ctx, const char *key, int value);
+
+const char *girih_gpu_strerror(int status);
+/* Detail of the last failure on this context (CUDA/NCCL error string); never NULL. */
+const char *girih_gpu_last_error(girih_gpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIRIH_CUDA_H_ */

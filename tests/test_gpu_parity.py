@@ -1,0 +1,331 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the committed reference
+outputs.  Bit-exact: the bar for this path is the reference's own (src/verification.c:842,
+L1 error == 0), which is stricter than the north star's relative L-inf tolerances
+(1e-12 fp64 / 1e-5 fp32) -- those are asserted as well, with the tolerance written out."""
+import hashlib
+import json
+import os
+import re
+import threading
+
+import numpy as np
+import pytest
+
+import girih_b200 as G
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SMALL = np.load(os.path.join(HERE, "golden", "small.npz"))
+SUMS = json.load(open(os.path.join(HERE, "golden", "checksums.json")))
+KEY = re.compile(r"k(\d)_(\d+)x(\d+)x(\d+)_nt(\d+)_ts(\d)_td(\d)_(sp|dp)$")
+TOL = {np.dtype(np.float64): 1e-12, np.dtype(np.float32): 1e-5}   # north star, relative L-inf
+
+
+def parse(key):
+    m = KEY.match(key)
+    k, nx, ny, nz, nt, ts, td = (int(g) for g in m.groups()[:7])
+    return k, (nx, ny, nz), nt, ts, td, np.dtype(np.float32 if m.group(8) == "sp" else np.float64)
+
+
+def gpu_run(kernel, st, dt, ts, nt, t_dim=1, tfuse=0, options=()):
+    pb = G.make_problem(kernel, st, dt)
+    s = G.GpuStepper.for_problem(pb)
+    for k, v in options:
+        s.set_option(k, v)
+    nt_eff = s.run_ts(ts, nt, t_dim, tfuse)
+    s.download(pb.U1, pb.U2)
+    info = s.launch_info()
+    s.close()
+    return pb, nt_eff, info
+
+
+def oracle_run(O, kernel, st, dt, ts, nt, t_dim=1):
+    ob = O.make_problem(kernel, st, dt)
+    if ts == 2:
+        nt = O.diamond_round_nt(nt, t_dim)
+        O.run_steps(ob, nt - 1)
+    else:
+        O.run_naive(ob, nt)
+    return ob
+
+
+def assert_same(pb, ob):
+    rel = 0.0
+    if pb.U1.tobytes() != ob.U1.tobytes():
+        d = np.abs(pb.U1.astype(np.float64) - ob.U1.astype(np.float64)).max()
+        rel = d / max(np.abs(ob.U1).max(), 1e-300)
+    assert rel <= TOL[pb.dtype], f"relative Linf {rel}"
+    assert pb.U1.tobytes() == ob.U1.tobytes(), "U1 differs from the oracle (bit-exact expected)"
+    assert pb.U2.tobytes() == ob.U2.tobytes(), "U2 differs from the oracle (bit-exact expected)"
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key", sorted(k for k in SMALL.files if not k.endswith("_nteff")))
+def test_golden_small(key):
+    """GPU vs outputs of the unmodified reference (tests/golden/small.npz)."""
+    k, st, nt, ts, td, dt = parse(key)
+    pb, nte, _ = gpu_run(k, st, dt, ts, nt, td)
+    if ts == 2:
+        assert nte == int(SMALL[key + "_nteff"])
+    assert pb.interior().tobytes() == SMALL[key].tobytes()
+
+
+@pytest.mark.parametrize("key", sorted(SUMS))
+def test_golden_checksums(key):
+    k, st, nt, ts, td, dt = parse(key)
+    pb, nte, _ = gpu_run(k, st, dt, ts, nt, td)
+    assert nte == SUMS[key]["nt_effective"]
+    got = np.ascontiguousarray(pb.interior())
+    assert hashlib.sha256(got.tobytes()).hexdigest() == SUMS[key]["sha256"]
+
+
+# the reference's regression matrix, scripts/verification/verification_std.py:8-34 (single rank):
+# local dims {16,32,64} permutations x kernels 0-5, nt = max(10, nx/r/2) (verification_utils.py:14)
+DIMS = [(16, 32, 64), (32, 64, 16), (64, 16, 32)]
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 3, 4, 5, 7])
+@pytest.mark.parametrize("ts", [0, 1])
+def test_verification_std_matrix(oracle, ts, kernel, dt):
+    r = G.kernel_info(kernel).r
+    for st in DIMS:
+        nt = max(10, st[0] // r // 2)
+        pb, _, _ = gpu_run(kernel, st, dt, ts, nt)
+        assert_same(pb, oracle_run(oracle, kernel, st, dt, ts, nt))
+
+
+# scripts/verification/verification_idiam.py:11-23,65-103: diamond stepper, t_dim in {1,3,7}
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("kernel,t_dim", [(1, 1), (1, 3), (1, 7), (2, 3), (3, 1), (5, 3), (0, 1), (4, 1), (7, 1)])
+def test_verification_idiam_matrix(oracle, kernel, t_dim, dt):
+    r = G.kernel_info(kernel).r
+    st = (32, (t_dim + 1) * 2 * r * 2, max(32, 2 * t_dim * r + 8))
+    nt = max(10, st[0] // r // 2)
+    pb, nte, info = gpu_run(kernel, st, dt, 2, nt, t_dim)
+    assert info["steps"] == nte - 1
+    assert_same(pb, oracle_run(oracle, kernel, st, dt, 2, nt, t_dim))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 5])
+@pytest.mark.parametrize("tfuse", [1, 2, 3, 4])
+def test_fused_depths(oracle, kernel, tfuse, dt):
+    """every fusion depth, domain spanning several tiles in x and y, ragged sizes, odd step counts"""
+    for st, nsteps in (((150, 71, 23), 9), ((61, 34, 9), 12)):
+        pb = G.make_problem(kernel, st, dt)
+        s = G.GpuStepper.for_problem(pb)
+        s.run_fused(nsteps, tfuse)
+        assert s.launch_info()["steps"] == nsteps
+        s.download(pb.U1, pb.U2)
+        s.close()
+        ob = oracle.make_problem(kernel, st, dt)
+        oracle.run_steps(ob, nsteps)
+        assert_same(pb, ob)
+
+
+@pytest.mark.parametrize("tile", [408, 216, 412])
+@pytest.mark.parametrize("zchunk", [3, 8, 1000])
+def test_tiles_and_z_chunks(oracle, tile, zchunk):
+    st, nsteps = (70, 75, 29), 8
+    ob = oracle.make_problem(1, st, np.float64)
+    oracle.run_steps(ob, nsteps)
+    for tf in (1, 3, 4):
+        pb = G.make_problem(1, st, np.float64)
+        s = G.GpuStepper.for_problem(pb)
+        s.set_option("tile", tile)
+        s.set_option("zchunk", zchunk)
+        s.run_fused(nsteps, tf)
+        s.download(pb.U1, pb.U2)
+        s.close()
+        assert_same(pb, ob)
+
+
+@pytest.mark.parametrize("kernel", [0, 4])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_radius4_tile_seams(oracle, kernel, dt):
+    for st in ((140, 37, 21), (9, 5, 11), (257, 17, 10)):
+        pb, _, _ = gpu_run(kernel, st, dt, 0, 6, options=(("zchunk", 4),))
+        assert_same(pb, oracle_run(oracle, kernel, st, dt, 0, 6))
+
+
+@pytest.mark.parametrize("kernel", [0, 1, 2, 3, 4, 5, 7])
+def test_naive_variant_and_edge_sizes(oracle, kernel):
+    """tiny and degenerate domains (1 cell wide), naive kernels vs streamed kernels vs oracle"""
+    for st in ((1, 1, 1), (2, 3, 1), (5, 1, 7), (17, 3, 2)):
+        ob = oracle_run(oracle, kernel, st, np.float64, 0, 4)
+        for variant in (0, 1):
+            pb, _, _ = gpu_run(kernel, st, np.float64, 0, 4, options=(("variant", variant),))
+            assert_same(pb, ob)
+
+
+def test_step_box_is_the_operator_contract(oracle):
+    """girih_gpu_step_box == spt_blk_func_t over an arbitrary box (stencils_spt_blk.ic:19-48)"""
+    st = (20, 14, 12)
+    for kernel in (0, 1, 5):
+        pb = G.make_problem(kernel, st, np.float64)
+        ob = oracle.make_problem(kernel, st, np.float64)
+        r = pb.r
+        box = (r + 2, r + 1, r + 3, r + 15, r + 9, r + 10)
+        s = G.GpuStepper.for_problem(pb)
+        s.step_box(1, box)
+        s.download(pb.U1, pb.U2)
+        s.close()
+        oracle.step(kernel, ob.shape, box, ob.coef, ob.U1, ob.U2, ob.U3)
+        assert_same(pb, ob)
+
+
+def test_repeated_runs_keep_evolving_like_the_reference(oracle):
+    """performance_test() does not re-initialise between tests (src/performance.c:50-52,70)"""
+    st = (40, 24, 20)
+    pb = G.make_problem(1, st, np.float64)
+    ob = oracle.make_problem(1, st, np.float64)
+    s = G.GpuStepper.for_problem(pb)
+    for _ in range(3):
+        s.run_fused(9, 4)
+        oracle.run_steps(ob, 9)
+    s.download(pb.U1, pb.U2)
+    s.close()
+    assert_same(pb, ob)
+
+
+def test_frame_mismatch_is_reported():
+    pb = G.make_problem(1, (16, 16, 16), np.float64)
+    pb.U2[0, 0, 0] += 1.0
+    s = G.GpuStepper.for_problem(pb)
+    with pytest.raises(G.GirihError) as e:
+        s.run_fused(8, 4)
+    assert e.value.status == 7
+    s.run_fused(8, 1)      # single-step passes need no such assumption
+    s.close()
+
+
+def test_scan_counts_nan_and_zero(oracle):
+    pb = G.make_problem(0, (24, 24, 24), np.float32)
+    s = G.GpuStepper.for_problem(pb)
+    s.run_single(120)       # the default coefficients overflow fp32 by then
+    s.download(pb.U1, None)
+    nans, zeros = s.scan_u1()
+    s.close()
+    assert nans == int((pb.U1 * 0 != 0).sum()) and nans > 0
+    assert zeros == int((np.abs(pb.U1) < 1e-6).sum())
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs): schedule independence, frame invariance
+# ------------------------------------------------------------------------------------------------
+def test_full_size_fused_equals_single_step_512():
+    st = (512, 512, 512)
+    pb = G.make_problem(1, st, np.float64)
+    frame_before = pb.U1[0].copy(), pb.U1[:, 0].copy(), pb.U1[:, :, 0].copy()
+    s = G.GpuStepper.for_problem(pb)
+    s.run_single(13)
+    a1, a2 = np.empty_like(pb.U1), np.empty_like(pb.U1)
+    s.download(a1, a2)
+    s.upload(pb)
+    s.run_fused(13, 4)
+    b1, b2 = np.empty_like(pb.U1), np.empty_like(pb.U1)
+    s.download(b1, b2)
+    s.close()
+    assert a1.tobytes() == b1.tobytes() and a2.tobytes() == b2.tobytes()
+    assert np.array_equal(a1[0], frame_before[0]) and np.array_equal(a1[:, 0], frame_before[1])
+    assert np.array_equal(a1[:, :, 0], frame_before[2])
+    assert np.isfinite(a1).all() and np.abs(a1[1:-1, 1:-1, 1:513]).max() > 1.0
+
+
+def test_full_size_streamed_equals_naive_k0_fp32_384():
+    st = (384, 384, 384)
+    pb = G.make_problem(0, st, np.float32)
+    s = G.GpuStepper.for_problem(pb)
+    s.run_single(6)
+    a1 = np.empty_like(pb.U1)
+    s.download(a1, None)
+    s.upload(pb)
+    s.set_option("variant", 1)
+    s.run_single(6)
+    b1 = np.empty_like(pb.U1)
+    s.download(b1, None)
+    s.close()
+    assert a1.tobytes() == b1.tobytes()
+
+
+# ------------------------------------------------------------------------------------------------
+# the executable: --verify 1 prints the reference's verdict line (src/verification.c:851-852,936-949)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("ts,kernel,extra", [(0, 0, ()), (0, 1, ()), (1, 4, ()), (2, 1, ("--t-dim", 3)),
+                                             (2, 5, ("--t-dim", 1, "--mwd-type", 2)), (2, 0, ("--t-dim", 1)),
+                                             (0, 7, ())])
+def test_cli_verify(ts, kernel, extra, dt):
+    rc, out, err = G.run_reference_cli(dt, ["--nx", 48, "--ny", 32, "--nz", 40, "--nt", 20, "--target-ts", ts,
+                                            "--target-kernel", kernel, "--verify", 1, "--verbose", 0, *extra])
+    assert rc == 0, out + err
+    assert "eMax:0.000e+00|eL1:0.000e+00-PASSED" in out
+    assert out.startswith("#ts:" + ["Spatial Blocking", "Halo-first", "Diamond"][ts])
+
+
+def test_cli_performance_schema():
+    rc, out, err = G.run_reference_cli(np.float64, ["--nx", 128, "--ny", 128, "--nz", 128, "--nt", 50,
+                                                    "--target-ts", 2, "--target-kernel", 1, "--t-dim", 7,
+                                                    "--n-tests", 2])
+    assert rc == 0, out + err
+    for key in ("Time stepper name: Diamond", "Number of time steps: 66", "Total RANK0 MStencil/s MAX:",
+                "MWD main-loop RANK0 MStencil/s MAX:", "GPU true GLUP/s", "COMPLETED SUCCESSFULLY"):
+        assert key in out, key
+    rc, out, err = G.run_reference_cli(np.float32, ["--nx", 128, "--ny", 64, "--nz", 64, "--nt", 20, "--n-tests", 2])
+    assert rc == 0 and "RANK0 GStencil/s    MAX:" in out and "RANK0 Computation:" in out
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-GPU (needs >= 2 devices; one host thread per GPU like mwd_kernel --npz)
+# ------------------------------------------------------------------------------------------------
+def _multi_gpu_run(kernel, gst, dt, nranks, fn):
+    uid = G.GpuStepper.comm_unique_id()
+    out, errs = [None] * nranks, []
+
+    def work(rank):
+        try:
+            pb = G.make_problem(kernel, gst, dt, rank=rank, nranks=nranks)
+            s = G.GpuStepper(kernel, pb.stencil, pb.shape, dt, device=rank, rank=rank, nranks=nranks)
+            s.comm_init(uid)
+            s.upload(pb)
+            fn(s)
+            s.download(pb.U1, pb.U2)
+            s.close()
+            out[rank] = pb
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    if errs:
+        raise errs[0]
+    return out
+
+
+@pytest.mark.parametrize("kernel,tfuse", [(1, 1), (1, 4), (0, 1), (5, 3), (4, 1)])
+def test_z_slabs_match_global_oracle(oracle, kernel, tfuse):
+    n = min(G.gpu_count(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    gst, dt, nsteps = (40, 24, 16 * n + 3), np.float64, 11
+    for overlap in (0, 1):
+        def fn(s):
+            s.set_option("overlap", overlap)
+            if tfuse == 1:
+                s.run_single(nsteps, overlap=bool(overlap))
+            else:
+                s.run_fused(nsteps, tfuse)
+        slabs = _multi_gpu_run(kernel, gst, dt, n, fn)
+        ob = oracle.make_problem(kernel, gst, dt)
+        oracle.run_steps(ob, nsteps)
+        r = ob.r
+        for pb in slabs:
+            z0 = pb.gb[2]
+            lnz = pb.stencil[2]
+            # interior planes of both arrays; halo planes of the newest array (exchanged at the end)
+            assert np.array_equal(pb.U1[r:r + lnz], ob.U1[z0 + r:z0 + r + lnz])
+            assert np.array_equal(pb.U2[r:r + lnz], ob.U2[z0 + r:z0 + r + lnz])
+            assert np.array_equal(pb.U1, ob.U1[z0:z0 + lnz + 2 * r])
