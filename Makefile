@@ -18,9 +18,15 @@ LIB       := girih_b200/libgirih_cuda.so
 .PHONY: all lib host oracle clean
 all: lib host
 
+CU_SRC    := $(wildcard $(CSRC)/*.cu)
+CU_OBJ    := $(patsubst $(CSRC)/%.cu,$(CSRC)/obj/%.o,$(CU_SRC))
+
 lib: $(LIB)
-$(LIB): $(CUDA_DEPS)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/girih_cuda.cu -ldl
+$(CSRC)/obj/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/girih_cuda.h
+	@mkdir -p $(CSRC)/obj
+	$(NVCC) $(NVFLAGS) $(PTXASV) -c -o $@ $<
+$(LIB): $(CU_OBJ)
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $(CU_OBJ) -ldl
 
 host: build/mwd_kernel build_dp/mwd_kernel girih_b200/libgirih_host_sp.so girih_b200/libgirih_host_dp.so
 
@@ -43,4 +49,4 @@ oracle:
 	if [ -d /root/reference/src ]; then $(MAKE) -C oracle ref -j8; fi
 
 clean:
-	rm -rf build build_dp girih_b200/*.so
+	rm -rf build build_dp girih_b200/*.so girih_b200/csrc/obj

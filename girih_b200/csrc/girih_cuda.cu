@@ -18,8 +18,7 @@
 
 #include "common.cuh"
 #include "kernels_naive.cuh"
-#include "kernels_r1.cuh"
-#include "kernels_r4.cuh"
+#include "launch.h"
 #include "nccl_dyn.h"
 #include "stencil_expr.cuh"
 
@@ -194,6 +193,7 @@ extern "C" int girih_gpu_create(girih_gpu_ctx **out, int device, int target_kern
   if (e == cudaSuccess) e = cudaEventCreate(&c->ev_t1);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_y, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();   // memsets above are asynchronous to the host
   if (e != cudaSuccess) {
     fprintf(stderr, "girih_gpu_create: %s\n", cudaGetErrorString(e));
     return bail(GIRIH_ERR_CUDA);
@@ -244,8 +244,8 @@ static cudaError_t copy3d(girih_gpu_ctx *c, void *dev, const void *host_c, bool 
   void *host = const_cast<void *>(host_c);
   cudaMemcpy3DParms p;
   memset(&p, 0, sizeof(p));
-  cudaPitchedPtr hp = make_cudaPitchedPtr(host, (size_t)c->hshape[0] * es, c->hshape[0], c->hshape[1]);
-  cudaPitchedPtr dp = make_cudaPitchedPtr(dev, (size_t)g.px * es, g.px, g.ny_dev);
+  cudaPitchedPtr hp = make_cudaPitchedPtr(host, (size_t)c->hshape[0] * es, (size_t)c->hshape[0] * es, c->hshape[1]);
+  cudaPitchedPtr dp = make_cudaPitchedPtr(dev, (size_t)g.px * es, (size_t)g.px * es, g.ny_dev);
   cudaPos hpos = make_cudaPos(0, 0, 0);
   cudaPos dpos = make_cudaPos((size_t)(g.X0 - r) * es, g.Y0 - r, g.Z0 - r);
   p.extent = make_cudaExtent((size_t)(g.nx + 2 * r) * es, c->hshape[1], c->hshape[2]);
@@ -283,13 +283,17 @@ extern "C" int girih_gpu_upload(girih_gpu_ctx *c, const void *U1, const void *U2
   if (c->kd.time_order == 2 && !U3) return fail(c, GIRIH_ERR_ARG, "U3 (roc2) is required for time_order 2");
   if ((c->kd.n_coef_arrays > 0 || c->kd.n_coef_scalars > 0) && !coef) return fail(c, GIRIH_ERR_ARG, "coef is required");
   CU(cudaSetDevice(c->device));
-  CU(copy3d(c, c->dU[0], U1, true, 0, false));
-  CU(copy3d(c, c->dU[1], U2, true, 0, false));
-  if (c->kd.time_order == 2) CU(copy3d(c, c->dU3, U3, true, 0, false));
+  // All transfers go through the context's own (non-blocking) stream: a synchronous cudaMemcpy from
+  // pageable memory may return while the DMA is still in flight, and kernels on a non-blocking stream
+  // are not ordered behind the legacy default stream.
+  CU(copy3d(c, c->dU[0], U1, true, c->s_comp, true));
+  CU(copy3d(c, c->dU[1], U2, true, c->s_comp, true));
+  if (c->kd.time_order == 2) CU(copy3d(c, c->dU3, U3, true, c->s_comp, true));
   const size_t ln = (size_t)c->hshape[0] * c->hshape[1] * c->hshape[2];
   for (int m = 0; m < c->kd.n_coef_arrays; ++m)
     CU(copy3d(c, (char *)c->dCoef + (size_t)m * c->arr_elems * c->es,
-              (const char *)coef + (size_t)m * ln * c->es, true, 0, false));
+              (const char *)coef + (size_t)m * ln * c->es, true, c->s_comp, true));
+  CU(cudaStreamSynchronize(c->s_comp));
   for (int m = 0; m < c->kd.n_coef_scalars; ++m)
     c->cc[m] = (c->es == 8) ? ((const double *)coef)[m] : (double)((const float *)coef)[m];
   c->frames_equal = (c->es == 8) ? frames_match(c, (const double *)U1, (const double *)U2)
@@ -312,8 +316,8 @@ extern "C" int girih_gpu_download(girih_gpu_ctx *c, void *U1, void *U2) {
   if (!c) return GIRIH_ERR_ARG;
   if (!c->uploaded) return fail(c, GIRIH_ERR_STATE, "download before upload");
   CU(cudaSetDevice(c->device));
-  if (U1) CU(copy3d(c, U1, c->dU[0], false, c->s_comp, true));
-  if (U2) CU(copy3d(c, U2, c->dU[1], false, c->s_comp, true));
+  if (U1) CU(copy3d(c, c->dU[0], U1, false, c->s_comp, true));
+  if (U2) CU(copy3d(c, c->dU[1], U2, false, c->s_comp, true));
   CU(cudaStreamSynchronize(c->s_comp));
   return GIRIH_OK;
 }
@@ -431,97 +435,6 @@ static cudaError_t launch_naive(girih_gpu_ctx *c, int dst, int xb, int yb, int z
 #undef GN
 }
 
-// ---- radius-1 streamed / fused ----------------------------------------------------------------
-struct TileChoice { int py, nw; };
-
-template <int K, typename R, int T, int PY, int NW>
-static cudaError_t launch_r1_t(girih_gpu_ctx *c, int src, int dst, int zb0, int ze0) {
-  using Cfg = R1Cfg<R, T, PY, NW>;
-  const DevGrid &g = c->g;
-  R1Args<R> a;
-  a.g = g;
-  a.in = (const R *)c->dU[src];
-  a.out = (R *)c->dU[dst];
-  a.coef = (const R *)c->dCoef;
-  a.coef_stride = (long long)c->arr_elems;
-  a.cc = make_cc<R>(c);
-  a.zb0 = zb0; a.ze0 = ze0;
-  const int ntx = (g.nx + Cfg::UX - 1) / Cfg::UX, nty = (g.ny + Cfg::UY - 1) / Cfg::UY;
-  int zchunk = c->opt_zchunk;
-  if (zchunk <= 0) {
-    // aim for >= ~6 waves of CTAs over 148 SMs while keeping the 2T-plane pipeline fill per chunk small
-    const int nz = ze0 - zb0;
-    const int want = 148 * 6;
-    int nch = std::max(1, (want + ntx * nty - 1) / (ntx * nty));
-    zchunk = std::max(std::min(nz, 16 * T), (nz + nch - 1) / nch);
-  }
-  a.zchunk = zchunk;
-  dim3 grid(ntx, nty, (ze0 - zb0 + zchunk - 1) / zchunk);
-  auto kfn = k_r1<K, R, T, PY, NW>;
-  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-  if (e != cudaSuccess) return e;
-  kfn<<<grid, 32 * NW, Cfg::SMEM, c->s_comp>>>(a);
-  c->n_kernels++;
-  return cudaGetLastError();
-}
-
-template <int K, typename R, int T>
-static cudaError_t launch_r1_tile(girih_gpu_ctx *c, int src, int dst, int zb0, int ze0) {
-  // tile shapes instantiated per (operator, precision, depth); "tile" option = PY*100 + NW
-  const int tile = c->opt_tile;
-  if constexpr (KTraits<K>::NCA == 0) {
-    if (tile == 216) return launch_r1_t<K, R, T, 2, 16>(c, src, dst, zb0, ze0);
-    if (tile == 412) return launch_r1_t<K, R, T, 4, 12>(c, src, dst, zb0, ze0);
-    return launch_r1_t<K, R, T, 4, 8>(c, src, dst, zb0, ze0);
-  } else {
-    if (tile == 408) return launch_r1_t<K, R, T, 4, 8>(c, src, dst, zb0, ze0);
-    return launch_r1_t<K, R, T, 2, 16>(c, src, dst, zb0, ze0);
-  }
-}
-
-template <int K, typename R>
-static cudaError_t launch_r1_depth(girih_gpu_ctx *c, int T, int src, int dst, int zb0, int ze0) {
-  switch (T) {
-    case 1: return launch_r1_tile<K, R, 1>(c, src, dst, zb0, ze0);
-    case 2: return launch_r1_tile<K, R, 2>(c, src, dst, zb0, ze0);
-    case 3: return launch_r1_tile<K, R, 3>(c, src, dst, zb0, ze0);
-    case 4: return launch_r1_tile<K, R, 4>(c, src, dst, zb0, ze0);
-    default: return cudaErrorInvalidValue;
-  }
-}
-
-// ---- radius-4 streamed --------------------------------------------------------------------------
-template <int K, typename R, int PY, int NW>
-static cudaError_t launch_r4_t(girih_gpu_ctx *c, int src, int dst, int zb0, int ze0) {
-  using Cfg = R4Cfg<R, PY, NW>;
-  const DevGrid &g = c->g;
-  R4Args<R> a;
-  a.g = g;
-  a.v = (const R *)c->dU[src];
-  a.u = (R *)c->dU[dst];
-  a.roc2 = (const R *)c->dU3;
-  a.coef = (const R *)c->dCoef;
-  a.coef_stride = (long long)c->arr_elems;
-  a.cc = make_cc<R>(c);
-  a.zb0 = zb0; a.ze0 = ze0;
-  const int ntx = (g.nx + Cfg::WX - 1) / Cfg::WX, nty = (g.ny + Cfg::H - 1) / Cfg::H;
-  int zchunk = c->opt_zchunk;
-  if (zchunk <= 0) {
-    const int nz = ze0 - zb0;
-    const int want = 148 * 8;
-    int nch = std::max(1, (want + ntx * nty - 1) / (ntx * nty));
-    zchunk = std::max(std::min(nz, 32), (nz + nch - 1) / nch);
-  }
-  a.zchunk = zchunk;
-  dim3 grid(ntx, nty, (ze0 - zb0 + zchunk - 1) / zchunk);
-  auto kfn = k_r4<K, R, PY, NW>;
-  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-  if (e != cudaSuccess) return e;
-  kfn<<<grid, 32 * NW, Cfg::SMEM, c->s_comp>>>(a);
-  c->n_kernels++;
-  return cudaGetLastError();
-}
-
 // One fused pass: T steps reading array `src` and writing array `dst` (src != dst) on the output
 // planes [zb0, ze0) (device z).  T == 1 is the single step of ts 0/1.
 static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb0, int ze0) {
@@ -532,18 +445,23 @@ static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb
     if (T != 1) return cudaErrorInvalidValue;
     return launch_naive(c, dst, g.X0, g.Y0, zb0, g.X0 + g.nx, g.Y0 + g.ny, ze0);
   }
-#define R1(K)                                                                              \
-  case K:                                                                                  \
-    return c->es == 8 ? launch_r1_depth<K, double>(c, T, src, dst, zb0, ze0)               \
-                      : launch_r1_depth<K, float>(c, T, src, dst, zb0, ze0);
-#define R4(K)                                                                              \
-  case K:                                                                                  \
-    if (T != 1) return cudaErrorInvalidValue;                                              \
-    return c->es == 8 ? launch_r4_t<K, double, 2, 8>(c, src, dst, zb0, ze0)                \
-                      : launch_r4_t<K, float, 2, 8>(c, src, dst, zb0, ze0);
-  switch (c->kernel) { R4(0) R1(1) R1(2) R1(3) R4(4) R1(5) default: return cudaErrorInvalidValue; }
-#undef R1
-#undef R4
+  StreamLaunch sl;
+  sl.g = g;
+  sl.in = c->dU[src];
+  sl.out = c->dU[dst];
+  sl.roc2 = c->dU3;
+  sl.coef = c->dCoef;
+  sl.coef_stride = (long long)c->arr_elems;
+  for (int i = 0; i < 5; ++i) sl.cc[i] = c->cc[i];
+  sl.zb0 = zb0;
+  sl.ze0 = ze0;
+  sl.zchunk = c->opt_zchunk;
+  sl.tile = c->opt_tile;
+  sl.stream = c->s_comp;
+  c->n_kernels++;
+  if (g.r == 1) return launch_r1(c->kernel, c->es, T, sl);
+  if (T != 1) return cudaErrorInvalidValue;
+  return launch_r4(c->kernel, c->es, sl);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,72 @@
+// inst_r1.cuh -- host-side launcher of k_r1 for one (operator, precision); included by the
+// inst_r1_k*_f*.cu translation units.
+#pragma once
+#include <algorithm>
+
+#include "kernels_r1.cuh"
+#include "launch.h"
+
+namespace girih {
+
+template <typename R> static inline ConstCoef<R> make_cc(const double (&cc)[5]) {
+  ConstCoef<R> k;
+  for (int i = 0; i < 5; ++i) k.v[i] = (R)cc[i];
+  return k;
+}
+
+template <int K, typename R, int T, int PY, int NW>
+static cudaError_t launch_r1_t(const StreamLaunch &s) {
+  using Cfg = R1Cfg<R, T, PY, NW>;
+  const DevGrid &g = s.g;
+  R1Args<R> a;
+  a.g = g;
+  a.in = (const R *)s.in;
+  a.out = (R *)s.out;
+  a.coef = (const R *)s.coef;
+  a.coef_stride = s.coef_stride;
+  a.cc = make_cc<R>(s.cc);
+  a.zb0 = s.zb0;
+  a.ze0 = s.ze0;
+  const int ntx = (g.nx + Cfg::UX - 1) / Cfg::UX, nty = (g.ny + Cfg::UY - 1) / Cfg::UY;
+  int zchunk = s.zchunk;
+  if (zchunk <= 0) {
+    // enough CTAs for several waves over 148 SMs, while keeping the 2T-plane pipeline fill of
+    // every z chunk small against the chunk itself
+    const int nz = s.ze0 - s.zb0;
+    const int want = 148 * Cfg::MINB * 4;
+    const int nch = std::max(1, (want + ntx * nty - 1) / (ntx * nty));
+    zchunk = std::max(std::min(nz, 24 * T), (nz + nch - 1) / nch);
+  }
+  a.zchunk = zchunk;
+  dim3 grid(ntx, nty, (s.ze0 - s.zb0 + zchunk - 1) / zchunk);
+  auto kfn = k_r1<K, R, T, PY, NW>;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  if (e != cudaSuccess) return e;
+  kfn<<<grid, 32 * NW, Cfg::SMEM, s.stream>>>(a);
+  return cudaGetLastError();
+}
+
+// tile shapes instantiated per (operator, precision, depth); "tile" option = PY*100 + NW
+template <int K, typename R, int T>
+static cudaError_t launch_r1_tile(const StreamLaunch &s) {
+  if (s.tile == 216) return launch_r1_t<K, R, T, 2, 16>(s);
+  if (s.tile == 408) return launch_r1_t<K, R, T, 4, 8>(s);
+  if constexpr (KTraits<K>::NCA == 0) return launch_r1_t<K, R, T, 4, 8>(s);
+  else return launch_r1_t<K, R, T, 2, 16>(s);
+}
+
+template <int K, typename R>
+static cudaError_t launch_r1_depth(int T, const StreamLaunch &s) {
+  switch (T) {
+    case 1: return launch_r1_tile<K, R, 1>(s);
+    case 2: return launch_r1_tile<K, R, 2>(s);
+    case 3: return launch_r1_tile<K, R, 3>(s);
+    case 4: return launch_r1_tile<K, R, 4>(s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+#define GIRIH_INST_R1(K, R, SUFFIX) \
+  cudaError_t launch_r1_##SUFFIX(int T, const StreamLaunch &s) { return launch_r1_depth<K, R>(T, s); }
+
+}  // namespace girih

@@ -65,6 +65,16 @@ template <typename R> struct RegNb1 {
   }
 };
 
+template <int PH> struct Phase { static constexpr int value = PH; };
+template <int I> struct Level { static constexpr int value = I; };
+template <bool B> struct FrameTag { static constexpr bool value = B; };
+template <int I, int N, typename F> __device__ __forceinline__ void static_for(F &&f) {
+  if constexpr (I < N) {
+    f(Level<I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
 template <int K, typename R, int T, int PY, int NW>
 __global__ void __launch_bounds__(32 * NW, R1Cfg<R, T, PY, NW>::MINB)
 k_r1(const R1Args<R> a) {
@@ -72,7 +82,9 @@ k_r1(const R1Args<R> a) {
   constexpr int VX = Cfg::VX, WX = Cfg::WX, HX = Cfg::HX, UX = Cfg::UX, H = Cfg::H, UY = Cfg::UY;
   constexpr int PF = Cfg::PF;
   constexpr int NCA = KTraits<K>::NCA;
+  constexpr unsigned ALL = (PY * VX >= 32) ? 0xffffffffu : ((1u << (PY * VX)) - 1u);
   static_assert(KTraits<K>::R == 1 && KTraits<K>::TO == 1, "radius-1, first-order-in-time only");
+  static_assert(PY * VX <= 32, "point masks are 32 bits");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // edge[l][parity][warp][0 = first row, 1 = last row][WX]
@@ -90,13 +102,15 @@ k_r1(const R1Args<R> a) {
 
   // per-point facts that do not change along z
   const bool x_alloc = (x >= 0) && (x + VX <= g.px);
-  bool row_alloc[PY];
+  unsigned row_alloc = 0;     // bit j: row j of my strip may be loaded
   unsigned interior_xy = 0;   // bit j*VX+e: point is an interior point in x and y
   unsigned core_xy = 0;       // ... and lies in this tile's core -> this tile stores it
 #pragma unroll
   for (int j = 0; j < PY; ++j) {
     const int y = y0 + j;
-    row_alloc[j] = x_alloc && (y >= 0) && (y < g.ny_dev);
+    // rows/columns past the domain (partial last tiles) are not read: nothing valid depends on them
+    if (x_alloc && (y >= 0) && (y < g.ny_dev) && (y < g.Y0 + g.ny + g.r) && (x < g.X0 + g.nx + g.r))
+      row_alloc |= 1u << j;
     const bool yin = (y >= g.Y0) && (y < g.Y0 + g.ny);
     const int ly = warp * PY + j;
     const bool ycore = (ly >= T) && (ly < H - T);
@@ -109,131 +123,167 @@ k_r1(const R1Args<R> a) {
       if (xin && yin && xcore && ycore) core_xy |= 1u << (j * VX + e);
     }
   }
+  // warps that lie completely inside the domain skip the per-point pass-through fix-up
+  const bool warp_masked = __any_sync(0xffffffffu, interior_xy != ALL);
   const long long row0 = (long long)y0 * g.px + x;   // offset of my first point inside a plane
+  // warp-uniform: can any plane this CTA touches be a frame plane, or does this warp touch the x/y frame?
+  const bool frame_possible = warp_masked || (zb - T < g.zlo) || (ze + T > g.zhi);
 
-  R B[T][PY][VX], C[T][PY][VX];
+  const int nit = (ze - zb) + 2 * T;
+
+  // The sweep exists twice: FRAME = false for warps that never see a non-interior point (no
+  // pass-through code at all), FRAME = true for warps on the domain boundary.  Both execute exactly one
+  // __syncthreads per z iteration, so warps of one CTA may run different versions.
+  auto sweep = [&](auto frame_tag) {
+    constexpr bool FRAME = decltype(frame_tag)::value;
+  // S[l][.] : three rotating register planes of level l.  In phase PH (= iteration mod 3)
+  //   S[l][PH] = plane zc-1 ("B"), S[l][(PH+1)%3] = plane zc ("C"), S[l][(PH+2)%3] = plane zc+1 ("F")
+  // where zc is the plane level l+1 is produced at in this iteration.  Level l+1 writes its new plane
+  // straight into S[l+1][(PH+2)%3]; the roles rotate with the unrolled phase, so no register moves.
+  R S[T][3][PY][VX];
 #pragma unroll
   for (int l = 0; l < T; ++l)
 #pragma unroll
-    for (int j = 0; j < PY; ++j)
-#pragma unroll
-      for (int e = 0; e < VX; ++e) { B[l][j][e] = (R)0; C[l][j][e] = (R)0; }
-
-  auto load_plane = [&](int z, R (&dst)[PY][VX]) {
-    const bool zok = (z >= 0) && (z < g.nz_dev);
-    const R *p = a.in + (long long)z * g.pxy + row0;
-#pragma unroll
-    for (int j = 0; j < PY; ++j) {
-      if (zok && row_alloc[j]) ld128<R>(p + (long long)j * g.px, dst[j]);
-      else {
-#pragma unroll
-        for (int e = 0; e < VX; ++e) dst[j][e] = (R)0;
-      }
-    }
-  };
-
-  R nxt[PF][PY][VX];
-#pragma unroll
-  for (int q = 0; q < PF; ++q) load_plane(zb - T + q, nxt[q]);
-
-  const int nit = (ze - zb) + 2 * T;
-  for (int it = 0; it < nit; ++it) {
-    const int zin = zb - T + it;
-    const int cur = it & 1;
-
-    R F[PY][VX];
-#pragma unroll
-    for (int j = 0; j < PY; ++j)
-#pragma unroll
-      for (int e = 0; e < VX; ++e) F[j][e] = nxt[0][j][e];
-#pragma unroll
-    for (int q = 0; q + 1 < PF; ++q)
+    for (int q = 0; q < 3; ++q)
 #pragma unroll
       for (int j = 0; j < PY; ++j)
 #pragma unroll
-        for (int e = 0; e < VX; ++e) nxt[q][j][e] = nxt[q + 1][j][e];
-    if (it + PF < nit) load_plane(zin + PF, nxt[PF - 1]);
+        for (int e = 0; e < VX; ++e) S[l][q][j][e] = (R)0;
+
+  // T == 1: PF planes are prefetched into a small queue.  T > 1: the next level-0 plane is loaded
+  // straight into the register plane that becomes "F" in the next phase (this phase's "B" of level 0,
+  // dead once level 1 has been produced), so the loads fly underneath levels 2..T.
+  R nxt[T == 1 ? PF : 1][PY][VX];
+#pragma unroll
+  for (int q = 0; q < (T == 1 ? PF : 1); ++q)
+#pragma unroll
+    for (int j = 0; j < PY; ++j)
+#pragma unroll
+      for (int e = 0; e < VX; ++e) nxt[q][j][e] = (R)0;
+
+  auto load_plane = [&](int z, R (&dst)[PY][VX]) {
+    if ((z >= 0) && (z < g.nz_dev)) {
+      const R *p = a.in + (long long)z * g.pxy + row0;
+#pragma unroll
+      for (int j = 0; j < PY; ++j)
+        if ((row_alloc >> j) & 1u) ld128<R>(p + (long long)j * g.px, dst[j]);
+    }
+  };
+  if constexpr (T == 1) {
+#pragma unroll
+    for (int q = 0; q < PF; ++q) load_plane(zb - T + q, nxt[q]);
+  } else {
+    load_plane(zb - T, S[0][2]);   // "F" of phase 0
+  }
+
+
+  auto body = [&](auto phase_tag, const int it) {
+    constexpr int PH = decltype(phase_tag)::value;
+    constexpr int iB = PH, iC = (PH + 1) % 3, iF = (PH + 2) % 3;
+    const int zin = zb - T + it;
+    const int cur = it & 1;
+
+    if constexpr (T == 1) {
+      // level 0: take the prefetched plane, keep the prefetch queue full
+#pragma unroll
+      for (int j = 0; j < PY; ++j)
+#pragma unroll
+        for (int e = 0; e < VX; ++e) S[0][iF][j][e] = nxt[0][j][e];
+#pragma unroll
+      for (int q = 0; q + 1 < PF; ++q)
+#pragma unroll
+        for (int j = 0; j < PY; ++j)
+#pragma unroll
+          for (int e = 0; e < VX; ++e) nxt[q][j][e] = nxt[q + 1][j][e];
+      if (it + PF < nit) load_plane(zin + PF, nxt[PF - 1]);
+    }
 
     // publish the first/last row of the level-0 plane for next iteration's level-1 update
-    st128<R>(edge_ptr(0, cur, warp, 0) + lane * VX, F[0]);
-    st128<R>(edge_ptr(0, cur, warp, 1) + lane * VX, F[PY - 1]);
+    st128<R>(edge_ptr(0, cur, warp, 0) + lane * VX, S[0][iF][0]);
+    st128<R>(edge_ptr(0, cur, warp, 1) + lane * VX, S[0][iF][PY - 1]);
 
-#pragma unroll
-    for (int l = 0; l < T; ++l) {
+    R Ofin[PY][VX];
+    static_for<0, T>([&](auto level_tag) {
+      constexpr int l = decltype(level_tag)::value;
       // level l+1 at plane zc from level l planes zc-1 (B), zc (C), zc+1 (F)
       const int zc = zin - l - 1;
-      const bool z_interior = (zc >= g.zlo) && (zc < g.zhi);
+      R (&Bp)[PY][VX] = S[l][iB];
+      R (&Cp)[PY][VX] = S[l][iC];
+      R (&Fp)[PY][VX] = S[l][iF];
 
       // rows just outside my strip, owned by the neighbouring warps (written last iteration)
       R up[VX], dn[VX];
       {
         const int wu = (warp > 0) ? warp - 1 : 0, wd = (warp < NW - 1) ? warp + 1 : NW - 1;
-        ld128s(edge_ptr(l, cur ^ 1, wu, 1) + lane * VX, up);
-        ld128s(edge_ptr(l, cur ^ 1, wd, 0) + lane * VX, dn);
+        ld128s<R>(edge_ptr(l, cur ^ 1, wu, 1) + lane * VX, up);
+        ld128s<R>(edge_ptr(l, cur ^ 1, wd, 0) + lane * VX, dn);
       }
 
-      // per-point coefficients of plane zc (slots 2, 3, 5)
-      R cf[NCA > 0 ? NCA : 1][PY][VX];
-      if constexpr (NCA > 0) {
-        const bool zok = (zc >= 0) && (zc < g.nz_dev);
-        const R *cp = a.coef + (long long)zc * g.pxy + row0;
-#pragma unroll
-        for (int m = 0; m < NCA; ++m)
-#pragma unroll
-          for (int j = 0; j < PY; ++j) {
-            if (zok && row_alloc[j]) ld128<R>(cp + (long long)m * a.coef_stride + (long long)j * g.px, cf[m][j]);
-            else {
-#pragma unroll
-              for (int e = 0; e < VX; ++e) cf[m][j][e] = (R)0;
-            }
-          }
-      }
-
-      R O[PY][VX];
+      auto stage = [&](R (&O)[PY][VX]) {
 #pragma unroll
       for (int j = 0; j < PY; ++j) {
-        const R left = __shfl_up_sync(0xffffffffu, C[l][j][VX - 1], 1);
-        const R right = __shfl_down_sync(0xffffffffu, C[l][j][0], 1);
+        // per-point coefficients of plane zc, row j (slots 2, 3, 5)
+        R cf[NCA > 0 ? NCA : 1][VX];
+        if constexpr (NCA > 0) {
+          const bool ok = (zc >= 0) && (zc < g.nz_dev) && ((row_alloc >> j) & 1u);
+          const R *cp = a.coef + (long long)zc * g.pxy + row0 + (long long)j * g.px;
+#pragma unroll
+          for (int m = 0; m < NCA; ++m) {
+#pragma unroll
+            for (int e = 0; e < VX; ++e) cf[m][e] = (R)0;
+            if (ok) ld128<R>(cp + (long long)m * a.coef_stride, cf[m]);
+          }
+        }
+        const R left = __shfl_up_sync(0xffffffffu, Cp[j][VX - 1], 1);
+        const R right = __shfl_down_sync(0xffffffffu, Cp[j][0], 1);
 #pragma unroll
         for (int e = 0; e < VX; ++e) {
           RegNb1<R> n;
-          n.c = C[l][j][e];
-          n.xm = (e > 0) ? C[l][j][e > 0 ? e - 1 : 0] : left;
-          n.xp = (e < VX - 1) ? C[l][j][e < VX - 1 ? e + 1 : 0] : right;
-          n.ym = (j > 0) ? C[l][j > 0 ? j - 1 : 0][e] : up[e];
-          n.yp = (j < PY - 1) ? C[l][j < PY - 1 ? j + 1 : 0][e] : dn[e];
-          n.zm = B[l][j][e];
-          n.zp = F[j][e];
-          R val;
+          n.c = Cp[j][e];
+          n.xm = (e > 0) ? Cp[j][e > 0 ? e - 1 : 0] : left;
+          n.xp = (e < VX - 1) ? Cp[j][e < VX - 1 ? e + 1 : 0] : right;
+          n.ym = (j > 0) ? Cp[j > 0 ? j - 1 : 0][e] : up[e];
+          n.yp = (j < PY - 1) ? Cp[j < PY - 1 ? j + 1 : 0][e] : dn[e];
+          n.zm = Bp[j][e];
+          n.zp = Fp[j][e];
           if constexpr (NCA > 0) {
             RegCoef<R, NCA> rc;
 #pragma unroll
-            for (int m = 0; m < NCA; ++m) rc.v[m] = cf[m][j][e];
-            val = StencilExpr<K>::template eval<R>(n, rc, (R)0, (R)0);
+            for (int m = 0; m < NCA; ++m) rc.v[m] = cf[m][e];
+            O[j][e] = StencilExpr<K>::template eval<R>(n, rc, (R)0, (R)0);
           } else {
-            val = StencilExpr<K>::template eval<R>(n, a.cc, (R)0, (R)0);
+            O[j][e] = StencilExpr<K>::template eval<R>(n, a.cc, (R)0, (R)0);
           }
-          const bool upd = z_interior && ((interior_xy >> (j * VX + e)) & 1u);
-          O[j][e] = upd ? val : n.c;
         }
       }
-
-      // rotate this level's z window and hand the new plane to the next level
+      // pass-through of everything that is not an interior point of the global domain
+      if constexpr (FRAME) {
+        if (!((zc >= g.zlo) && (zc < g.zhi))) {        // whole plane is frame: CTA-uniform
 #pragma unroll
-      for (int j = 0; j < PY; ++j)
+          for (int j = 0; j < PY; ++j)
 #pragma unroll
-        for (int e = 0; e < VX; ++e) {
-          B[l][j][e] = C[l][j][e];
-          C[l][j][e] = F[j][e];
-          F[j][e] = O[j][e];
+            for (int e = 0; e < VX; ++e) O[j][e] = Cp[j][e];
+        } else if (warp_masked) {                        // warp touches the x/y frame
+#pragma unroll
+          for (int j = 0; j < PY; ++j)
+#pragma unroll
+            for (int e = 0; e < VX; ++e)
+              if (!((interior_xy >> (j * VX + e)) & 1u)) O[j][e] = Cp[j][e];
         }
-      if (l + 1 < T) {
-        st128<R>(edge_ptr(l + 1, cur, warp, 0) + lane * VX, F[0]);
-        st128<R>(edge_ptr(l + 1, cur, warp, 1) + lane * VX, F[PY - 1]);
       }
-    }
+        if constexpr (l + 1 < T) {
+          st128<R>(edge_ptr(l + 1, cur, warp, 0) + lane * VX, O[0]);
+          st128<R>(edge_ptr(l + 1, cur, warp, 1) + lane * VX, O[PY - 1]);
+        }
+      };
+      if constexpr (l + 1 < T) stage(S[l + 1][iF]);
+      else stage(Ofin);
+      if constexpr (T > 1 && l == 0) {
+        if (it + 1 < nit) load_plane(zin + 1, S[0][iB]);   // next iteration's level-0 "F"
+      }
+    });
 
-    // F is level T at plane zin - T
+    // Ofin is level T at plane zin - T
     const int zo = zin - T;
     if (zo >= zb && zo < ze) {
       R *q = a.out + (long long)zo * g.pxy + row0;
@@ -241,16 +291,28 @@ k_r1(const R1Args<R> a) {
       for (int j = 0; j < PY; ++j) {
         const unsigned m = (core_xy >> (j * VX)) & ((1u << VX) - 1u);
         if (m == (1u << VX) - 1u) {
-          st128<R>(q + (long long)j * g.px, F[j]);
+          st128<R>(q + (long long)j * g.px, Ofin[j]);
         } else if (m != 0u) {
 #pragma unroll
           for (int e = 0; e < VX; ++e)
-            if ((m >> e) & 1u) q[(long long)j * g.px + e] = F[j][e];
+            if ((m >> e) & 1u) q[(long long)j * g.px + e] = Ofin[j][e];
         }
       }
     }
     __syncthreads();
+  };
+
+  int it = 0;
+  for (; it + 3 <= nit; it += 3) {
+    body(Phase<0>{}, it);
+    body(Phase<1>{}, it + 1);
+    body(Phase<2>{}, it + 2);
   }
+  if (it < nit) { body(Phase<0>{}, it); ++it; }
+  if (it < nit) { body(Phase<1>{}, it); }
+  };
+  if (frame_possible) sweep(FrameTag<true>{});
+  else sweep(FrameTag<false>{});
 }
 
 }  // namespace girih

@@ -1,0 +1,29 @@
+// launch.h -- interface between the context (girih_cuda.cu) and the per-operator kernel
+// translation units (inst_*.cu), which are compiled separately so the build parallelises.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace girih {
+
+struct StreamLaunch {
+  DevGrid g;
+  const void *in;        // array holding the newest level (read)
+  void *out;             // array written (slot 0: also read at the centre, level before `in`)
+  const void *roc2;      // slot 0
+  const void *coef;      // per-point coefficient arrays
+  long long coef_stride;
+  double cc[5];          // scalar coefficients
+  int zb0, ze0;          // output planes [zb0, ze0), device z
+  int zchunk;            // 0 = choose
+  int tile;              // 0 = default, else PY*100 + NW
+  cudaStream_t stream;
+};
+
+// T fused steps of a radius-1 operator (slots 1, 2, 3, 5); es = sizeof(real)
+cudaError_t launch_r1(int kernel, int es, int T, const StreamLaunch &a);
+// one step of a radius-4 operator (slots 0, 4)
+cudaError_t launch_r4(int kernel, int es, const StreamLaunch &a);
+
+}  // namespace girih

@@ -185,6 +185,10 @@ void arrays_allocate(Parameters *p) { /* src/utils.c:153-218 */
   p->U3 = NULL;
   if (p->stencil.time_order == 2) p->U3 = (real_t *)aligned_or_die(p, sizeof(real_t) * p->ln_domain);
   p->coef = (real_t *)aligned_or_die(p, sizeof(real_t) * coef_size);
+  /* The reference sets only coef[0..r] of a constant-coefficient operator (src/utils.c:441-444), so
+   * the box kernel (slot 7) reads coef[2] and coef[3] from untouched, i.e. zero, fresh pages.  Make
+   * that explicit instead of depending on the allocator. */
+  if (p->stencil.coeff == GIRIH_COEF_CONSTANT) memset(p->coef, 0, sizeof(real_t) * coef_size);
   if (p->verbose == 1 && (p->mpi_rank == 0 || p->mpi_rank == p->mpi_size - 1))
     printf("[rank=%d] alloc. dom(err=%d):%fGiB coef(err=%d):%fGiB total:%fGiB\n", p->mpi_rank, 0,
            sizeof(real_t) * 2.0 * p->ln_domain / (1024 * 1024 * 1024), 0,

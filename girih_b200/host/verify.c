@@ -84,7 +84,8 @@ static real_t *serial_reference(const Parameters *p, int shape[3]) {
   switch (p->stencil.coeff) { /* src/verification.c:92-197 */
     case GIRIH_COEF_CONSTANT:
       coef = (real_t *)xalloc(sizeof(real_t) * 11);
-      for (i = 0; i < (uint64_t)r + 1 || (p->stencil.shape == GIRIH_BOX && i < 4); i++) coef[i] = p->g_coef[i];
+      memset(coef, 0, sizeof(real_t) * 11);   /* box: coef[2..3] stay zero, see arrays_allocate() */
+      for (i = 0; i < (uint64_t)r + 1; i++) coef[i] = p->g_coef[i];
       break;
     case GIRIH_COEF_VARIABLE:
       csize = n * (uint64_t)(1 + r);

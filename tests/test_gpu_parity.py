@@ -266,7 +266,7 @@ def test_cli_verify(ts, kernel, extra, dt):
 
 
 def test_cli_performance_schema():
-    rc, out, err = G.run_reference_cli(np.float64, ["--nx", 128, "--ny", 128, "--nz", 128, "--nt", 50,
+    rc, out, err = G.run_reference_cli(np.float64, ["--nx", 128, "--ny", 128, "--nz", 128, "--nt", 52,
                                                     "--target-ts", 2, "--target-kernel", 1, "--t-dim", 7,
                                                     "--n-tests", 2])
     assert rc == 0, out + err
