@@ -28,20 +28,32 @@ static cudaError_t launch_r1_t(const StreamLaunch &s) {
   a.zb0 = s.zb0;
   a.ze0 = s.ze0;
   const int ntx = (g.nx + Cfg::UX - 1) / Cfg::UX, nty = (g.ny + Cfg::UY - 1) / Cfg::UY;
-  int zchunk = s.zchunk;
-  if (zchunk <= 0) {
-    // enough CTAs for several waves over 148 SMs, while keeping the 2T-plane pipeline fill of
-    // every z chunk small against the chunk itself
-    const int nz = s.ze0 - s.zb0;
-    const int want = 148 * Cfg::MINB * 4;
-    const int nch = std::max(1, (want + ntx * nty - 1) / (ntx * nty));
-    zchunk = std::max(std::min(nz, 24 * T), (nz + nch - 1) / nch);
-  }
-  a.zchunk = zchunk;
-  dim3 grid(ntx, nty, (s.ze0 - s.zb0 + zchunk - 1) / zchunk);
   auto kfn = k_r1<K, R, T, PY, NW>;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
   if (e != cudaSuccess) return e;
+  int zchunk = s.zchunk;
+  if (zchunk <= 0) {
+    // Split z into chunks so that the CTAs fill whole waves of the 148 SMs: every chunk pays 2T planes
+    // of pipeline fill, every partially filled last wave idles SMs.  Minimise
+    //   waves(ntiles * nch) * (ceil(nz / nch) + 2T).
+    int occ = 1, nsm = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, 32 * NW, Cfg::SMEM) != cudaSuccess || occ < 1) occ = 1;
+    const int nz = s.ze0 - s.zb0, ntiles = ntx * nty, slots = nsm * occ;
+    long long best = -1;
+    zchunk = nz;
+    for (int nch = 1; nch <= nz && nch <= 64; ++nch) {
+      const int zc = (nz + nch - 1) / nch;
+      if (zc < 4 * T && nch > 1) break;
+      const int real_nch = (nz + zc - 1) / zc;
+      const long long waves = ((long long)ntiles * real_nch + slots - 1) / slots;
+      const long long cost = waves * (zc + 2 * T);
+      if (best < 0 || cost < best) { best = cost; zchunk = zc; }
+    }
+  }
+  a.zchunk = zchunk;
+  dim3 grid(ntx, nty, (s.ze0 - s.zb0 + zchunk - 1) / zchunk);
   kfn<<<grid, 32 * NW, Cfg::SMEM, s.stream>>>(a);
   return cudaGetLastError();
 }

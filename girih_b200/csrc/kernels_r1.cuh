@@ -126,16 +126,13 @@ k_r1(const R1Args<R> a) {
   // warps that lie completely inside the domain skip the per-point pass-through fix-up
   const bool warp_masked = __any_sync(0xffffffffu, interior_xy != ALL);
   const long long row0 = (long long)y0 * g.px + x;   // offset of my first point inside a plane
-  // warp-uniform: can any plane this CTA touches be a frame plane, or does this warp touch the x/y frame?
-  const bool frame_possible = warp_masked || (zb - T < g.zlo) || (ze + T > g.zhi);
-
   const int nit = (ze - zb) + 2 * T;
 
-  // The sweep exists twice: FRAME = false for warps that never see a non-interior point (no
-  // pass-through code at all), FRAME = true for warps on the domain boundary.  Both execute exactly one
-  // __syncthreads per z iteration, so warps of one CTA may run different versions.
-  auto sweep = [&](auto frame_tag) {
-    constexpr bool FRAME = decltype(frame_tag)::value;
+  // The loop body exists twice: FRAME = false for iterations in which this warp cannot see a
+  // non-interior point (no pass-through code at all), FRAME = true for warps on the x/y frame and for
+  // the few iterations of the first/last z chunk whose planes touch the z frame.  Both versions execute
+  // exactly one __syncthreads per iteration, so the warps of a CTA may take different versions.
+  {
   // S[l][.] : three rotating register planes of level l.  In phase PH (= iteration mod 3)
   //   S[l][PH] = plane zc-1 ("B"), S[l][(PH+1)%3] = plane zc ("C"), S[l][(PH+2)%3] = plane zc+1 ("F")
   // where zc is the plane level l+1 is produced at in this iteration.  Level l+1 writes its new plane
@@ -177,8 +174,9 @@ k_r1(const R1Args<R> a) {
   }
 
 
-  auto body = [&](auto phase_tag, const int it) {
+  auto body = [&](auto phase_tag, auto frame_tag, const int it) {
     constexpr int PH = decltype(phase_tag)::value;
+    constexpr bool FRAME = decltype(frame_tag)::value;
     constexpr int iB = PH, iC = (PH + 1) % 3, iF = (PH + 2) % 3;
     const int zin = zb - T + it;
     const int cur = it & 1;
@@ -256,21 +254,15 @@ k_r1(const R1Args<R> a) {
           }
         }
       }
-      // pass-through of everything that is not an interior point of the global domain
-      if constexpr (FRAME) {
-        if (!((zc >= g.zlo) && (zc < g.zhi))) {        // whole plane is frame: CTA-uniform
+        // pass-through of everything that is not an interior point of the global domain: a frame
+        // plane clears the whole mask (CTA-uniform), the x/y frame clears single bits
+        if constexpr (FRAME) {
+          const unsigned upd = ((zc >= g.zlo) && (zc < g.zhi)) ? interior_xy : 0u;
 #pragma unroll
           for (int j = 0; j < PY; ++j)
 #pragma unroll
-            for (int e = 0; e < VX; ++e) O[j][e] = Cp[j][e];
-        } else if (warp_masked) {                        // warp touches the x/y frame
-#pragma unroll
-          for (int j = 0; j < PY; ++j)
-#pragma unroll
-            for (int e = 0; e < VX; ++e)
-              if (!((interior_xy >> (j * VX + e)) & 1u)) O[j][e] = Cp[j][e];
+            for (int e = 0; e < VX; ++e) O[j][e] = ((upd >> (j * VX + e)) & 1u) ? O[j][e] : Cp[j][e];
         }
-      }
         if constexpr (l + 1 < T) {
           st128<R>(edge_ptr(l + 1, cur, warp, 0) + lane * VX, O[0]);
           st128<R>(edge_ptr(l + 1, cur, warp, 1) + lane * VX, O[PY - 1]);
@@ -302,17 +294,21 @@ k_r1(const R1Args<R> a) {
     __syncthreads();
   };
 
+  // planes zin-T .. zin-1 are produced in iteration `it`; the version is chosen per iteration
+  auto step = [&](auto phase_tag, const int it) {
+    const int zin = zb - T + it;
+    if (warp_masked || (zin - T < g.zlo) || (zin > g.zhi)) body(phase_tag, FrameTag<true>{}, it);
+    else body(phase_tag, FrameTag<false>{}, it);
+  };
   int it = 0;
   for (; it + 3 <= nit; it += 3) {
-    body(Phase<0>{}, it);
-    body(Phase<1>{}, it + 1);
-    body(Phase<2>{}, it + 2);
+    step(Phase<0>{}, it);
+    step(Phase<1>{}, it + 1);
+    step(Phase<2>{}, it + 2);
   }
-  if (it < nit) { body(Phase<0>{}, it); ++it; }
-  if (it < nit) { body(Phase<1>{}, it); }
-  };
-  if (frame_possible) sweep(FrameTag<true>{});
-  else sweep(FrameTag<false>{});
+  if (it < nit) { step(Phase<0>{}, it); ++it; }
+  if (it < nit) { step(Phase<1>{}, it); }
+  }
 }
 
 }  // namespace girih
