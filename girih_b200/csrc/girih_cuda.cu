@@ -440,8 +440,12 @@ static cudaError_t launch_naive(girih_gpu_ctx *c, int dst, int xb, int yb, int z
 static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb0, int ze0) {
   const DevGrid &g = c->g;
   if (ze0 <= zb0) return cudaSuccess;
-  const bool streamed = (c->opt_variant != 1);
-  if (!streamed || c->kernel == 7) {
+  // variant 0 picks the fastest measured single-step kernel per operator and precision
+  // (profiles/kernel_sweep_r01.md): the marching kernel, except for the fp64 variable-coefficient
+  // operators where one thread per site with all loads in flight runs at the HBM limit already.
+  bool naive = (c->opt_variant == 1) || (c->kernel == 7);
+  if (c->opt_variant == 0 && T == 1 && c->es == 8 && (c->kernel == 2 || c->kernel == 3 || c->kernel == 5)) naive = true;
+  if (naive) {
     if (T != 1) return cudaErrorInvalidValue;
     return launch_naive(c, dst, g.X0, g.Y0, zb0, g.X0 + g.nx, g.Y0 + g.ny, ze0);
   }
@@ -457,6 +461,7 @@ static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb
   sl.ze0 = ze0;
   sl.zchunk = c->opt_zchunk;
   sl.tile = c->opt_tile;
+  sl.variant = c->opt_variant;
   sl.stream = c->s_comp;
   c->n_kernels++;
   if (g.r == 1) return launch_r1(c->kernel, c->es, T, sl);

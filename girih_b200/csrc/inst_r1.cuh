@@ -4,6 +4,7 @@
 #include <algorithm>
 
 #include "kernels_r1.cuh"
+#include "kernels_r1_march.cuh"
 #include "launch.h"
 
 namespace girih {
@@ -67,8 +68,47 @@ static cudaError_t launch_r1_tile(const StreamLaunch &s) {
   else return launch_r1_t<K, R, T, 2, 16>(s);
 }
 
+// single-step pass: the barrier-free marching kernel
+template <int K, typename R, int PY, int NWY>
+static cudaError_t launch_march_t(const StreamLaunch &s) {
+  const DevGrid &g = s.g;
+  constexpr int WX = 32 * Vec<R>::N;
+  MarchArgs<R> a;
+  a.g = g;
+  a.in = (const R *)s.in;
+  a.out = (R *)s.out;
+  a.coef = (const R *)s.coef;
+  a.coef_stride = s.coef_stride;
+  a.cc = make_cc<R>(s.cc);
+  a.zb0 = s.zb0;
+  a.ze0 = s.ze0;
+  const int nz = s.ze0 - s.zb0;
+  int zchunk = s.zchunk > 0 ? s.zchunk : 64;
+  // every chunk re-reads two planes; keep chunks long but leave >= ~8 waves of CTAs
+  constexpr int TY = PY * NWY;
+  const int ntiles = ((g.nx + WX - 1) / WX) * ((g.ny + TY - 1) / TY);
+  if (s.zchunk <= 0) {
+    while (zchunk < nz && (long long)ntiles * ((nz + zchunk - 1) / zchunk) > 148LL * 8 * 8) zchunk *= 2;
+    while (zchunk > 16 && (long long)ntiles * ((nz + zchunk - 1) / zchunk) < 148LL * 8 * 2) zchunk /= 2;
+  }
+  zchunk = std::min(zchunk, std::max(nz, 1));
+  a.zchunk = zchunk;
+  dim3 grid((g.nx + WX - 1) / WX, (g.ny + TY - 1) / TY, (nz + zchunk - 1) / zchunk);
+  k_r1_march<K, R, PY, NWY><<<grid, 32 * NWY, 0, s.stream>>>(a);
+  return cudaGetLastError();
+}
+
 template <int K, typename R>
 static cudaError_t launch_r1_depth(int T, const StreamLaunch &s) {
+  if (T == 1 && s.variant != 2) {
+    // tile option for the marching kernel: PY*100 + NWY
+    if (s.tile == 108) return launch_march_t<K, R, 1, 8>(s);
+    if (s.tile == 208) return launch_march_t<K, R, 2, 8>(s);
+    if (s.tile == 404) return launch_march_t<K, R, 4, 4>(s);
+    if (s.tile == 408) return launch_march_t<K, R, 4, 8>(s);
+    if constexpr (K == 1 || K == 5) return launch_march_t<K, R, 4, 4>(s);
+    else return launch_march_t<K, R, 2, 8>(s);
+  }
   switch (T) {
     case 1: return launch_r1_tile<K, R, 1>(s);
     case 2: return launch_r1_tile<K, R, 2>(s);

@@ -18,6 +18,7 @@ struct StreamLaunch {
   int zb0, ze0;          // output planes [zb0, ze0), device z
   int zchunk;            // 0 = choose
   int tile;              // 0 = default, else PY*100 + NW
+  int variant;           // 0 = auto, 2 = force the fused-sweep kernel also for T = 1
   cudaStream_t stream;
 };
 

@@ -162,8 +162,12 @@ int girih_gpu_time_pass(girih_gpu_ctx *ctx, int tfuse, int reps, double *ms_per_
  * (src/utils.c:819-840), done on the device. */
 int girih_gpu_scan_u1(girih_gpu_ctx *ctx, uint64_t *n_nan_inf, uint64_t *n_zero);
 
-/* Tuning knobs (all optional).  Keys: "variant" (0 auto, 1 naive, 2 streamed),
- * "zchunk" (output planes per CTA), "tile" (encoded PY*100+NW). */
+/* Tuning knobs (all optional).  Keys:
+ *   "variant"  0 auto (marching kernel for single steps, fused sweep for T > 1), 1 naive kernels,
+ *              2 fused-sweep kernel also for T = 1
+ *   "zchunk"   output planes per CTA (0 = choose)
+ *   "tile"     fused sweep: PY*100 + NW (rows per thread, warps per CTA); marching kernel: rows per CTA
+ *   "overlap"  overlap the halo exchange of fused passes with compute (default 1) */
 int girih_gpu_set_option(girih_gpu_ctx *ctx, const char *key, int value);
 
 const char *girih_gpu_strerror(int status);

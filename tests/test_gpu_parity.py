@@ -125,21 +125,41 @@ def test_fused_depths(oracle, kernel, tfuse, dt):
         assert_same(pb, ob)
 
 
-@pytest.mark.parametrize("tile", [408, 216, 412])
+@pytest.mark.parametrize("tile", [408, 216])
 @pytest.mark.parametrize("zchunk", [3, 8, 1000])
 def test_tiles_and_z_chunks(oracle, tile, zchunk):
+    """fused-sweep kernel: every tile shape x z chunking, also forced for single steps (variant 2)"""
     st, nsteps = (70, 75, 29), 8
     ob = oracle.make_problem(1, st, np.float64)
     oracle.run_steps(ob, nsteps)
     for tf in (1, 3, 4):
         pb = G.make_problem(1, st, np.float64)
         s = G.GpuStepper.for_problem(pb)
+        s.set_option("variant", 2)
         s.set_option("tile", tile)
         s.set_option("zchunk", zchunk)
         s.run_fused(nsteps, tf)
         s.download(pb.U1, pb.U2)
         s.close()
         assert_same(pb, ob)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 5])
+def test_marching_kernel_tiles(oracle, kernel, dt):
+    """single-step marching kernel: rows per CTA x z chunking x ragged sizes spanning several tiles"""
+    for st in ((150, 37, 23), (129, 9, 5), (64, 16, 70)):
+        ob = oracle.make_problem(kernel, st, dt)
+        oracle.run_steps(ob, 5)
+        for rows, zchunk in ((108, 0), (208, 7), (404, 1), (408, 3)):
+            pb = G.make_problem(kernel, st, dt)
+            s = G.GpuStepper.for_problem(pb)
+            s.set_option("tile", rows)
+            s.set_option("zchunk", zchunk)
+            s.run_single(5)
+            s.download(pb.U1, pb.U2)
+            s.close()
+            assert_same(pb, ob)
 
 
 @pytest.mark.parametrize("kernel", [0, 4])
