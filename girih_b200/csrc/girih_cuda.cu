@@ -31,10 +31,10 @@ static const girih_kernel_desc KERNELS[8] = {
     // name  r to nd shape       coeff                       nca ncs words tfuse gpu
     {"star", 4, 2, 3, GIRIH_STAR, GIRIH_COEF_CONSTANT, 0, 5, 4, 1, 1},
     {"star", 1, 1, 2, GIRIH_STAR, GIRIH_COEF_CONSTANT, 0, 2, 2, 4, 1},
-    {"star", 1, 1, 4, GIRIH_STAR, GIRIH_COEF_VARIABLE, 2, 0, 4, 4, 1},
-    {"star", 1, 1, 6, GIRIH_STAR, GIRIH_COEF_VARIABLE_AXSYM, 4, 0, 6, 4, 1},
+    {"star", 1, 1, 4, GIRIH_STAR, GIRIH_COEF_VARIABLE, 2, 0, 4, 3, 1},
+    {"star", 1, 1, 6, GIRIH_STAR, GIRIH_COEF_VARIABLE_AXSYM, 4, 0, 6, 3, 1},
     {"star", 4, 1, 15, GIRIH_STAR, GIRIH_COEF_VARIABLE_AXSYM, 13, 0, 15, 1, 1},
-    {"star", 1, 1, 9, GIRIH_STAR, GIRIH_COEF_VARIABLE_NOSYM, 7, 0, 9, 4, 1},
+    {"star", 1, 1, 9, GIRIH_STAR, GIRIH_COEF_VARIABLE_NOSYM, 7, 0, 9, 3, 1},
     {"star", 1, 1, 40, GIRIH_STAR, GIRIH_COEF_SOLAR, 0, 0, 40, 1, 0},
     {"box", 1, 1, 2, GIRIH_BOX, GIRIH_COEF_CONSTANT, 0, 4, 2, 1, 1},
 };
@@ -472,6 +472,19 @@ static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb
 // ------------------------------------------------------------------------------------------------
 // steppers
 // ------------------------------------------------------------------------------------------------
+// Fusion depth used when the caller does not ask for one: the fastest measured depth per operator
+// and precision on B200 at 512^3 (profiles/kernel_sweep_r01.md).  Constant coefficients gain most;
+// with per-point coefficient arrays the coefficient planes dominate the traffic and are re-read by
+// every fused level, so the gain shrinks (slot 2, 3) or vanishes (slot 5: 9 words per update).
+static int default_tfuse(const girih_gpu_ctx *c) {
+  switch (c->kernel) {
+    case 1: return 4;
+    case 2: return 3;
+    case 3: return c->es == 8 ? 2 : 3;
+    default: return 1;
+  }
+}
+
 static int begin_run(girih_gpu_ctx *c) {
   if (!c->uploaded) return fail(c, GIRIH_ERR_STATE, "run before upload");
   CU(cudaSetDevice(c->device));
@@ -572,7 +585,7 @@ extern "C" int girih_gpu_run_single(girih_gpu_ctx *c, int nsteps, int overlap) {
 extern "C" int girih_gpu_run_fused(girih_gpu_ctx *c, int nsteps, int tfuse) {
   if (!c || nsteps < 0) return GIRIH_ERR_ARG;
   int T = tfuse;
-  if (T <= 0) T = c->kd.max_tfuse;
+  if (T <= 0) T = default_tfuse(c);
   T = std::min(T, c->kd.max_tfuse);
   if (c->opt_variant == 1 || c->kernel == 7) T = 1;
   if (c->nranks > 1) T = std::min(T, std::max(1, c->g.nz / std::max(1, c->g.r)));

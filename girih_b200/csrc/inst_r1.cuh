@@ -15,7 +15,7 @@ template <typename R> static inline ConstCoef<R> make_cc(const double (&cc)[5]) 
   return k;
 }
 
-template <int K, typename R, int T, int PY, int NW>
+template <int K, typename R, int T, int PY, int NW, int DBG = 0>
 static cudaError_t launch_r1_t(const StreamLaunch &s) {
   using Cfg = R1Cfg<R, T, PY, NW>;
   const DevGrid &g = s.g;
@@ -29,7 +29,7 @@ static cudaError_t launch_r1_t(const StreamLaunch &s) {
   a.zb0 = s.zb0;
   a.ze0 = s.ze0;
   const int ntx = (g.nx + Cfg::UX - 1) / Cfg::UX, nty = (g.ny + Cfg::UY - 1) / Cfg::UY;
-  auto kfn = k_r1<K, R, T, PY, NW>;
+  auto kfn = k_r1<K, R, T, PY, NW, DBG>;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
   if (e != cudaSuccess) return e;
   int zchunk = s.zchunk;
@@ -64,7 +64,23 @@ template <int K, typename R, int T>
 static cudaError_t launch_r1_tile(const StreamLaunch &s) {
   if (s.tile == 216) return launch_r1_t<K, R, T, 2, 16>(s);
   if (s.tile == 408) return launch_r1_t<K, R, T, 4, 8>(s);
-  if constexpr (KTraits<K>::NCA == 0) return launch_r1_t<K, R, T, 4, 8>(s);
+  if constexpr (K == 1 && sizeof(R) == 8 && T == 4) {   // perf experiments only (results invalid)
+    if (s.tile == 1408) return launch_r1_t<K, R, T, 4, 8, 1>(s);
+    if (s.tile == 2408) return launch_r1_t<K, R, T, 4, 8, 2>(s);
+    if (s.tile == 3408) return launch_r1_t<K, R, T, 4, 8, 3>(s);
+    if (s.tile == 3216) return launch_r1_t<K, R, T, 2, 16, 3>(s);
+    if (s.tile == 3312) return launch_r1_t<K, R, T, 3, 12, 3>(s);
+    if (s.tile == 1216) return launch_r1_t<K, R, T, 2, 16, 1>(s);
+    if (s.tile == 2216) return launch_r1_t<K, R, T, 2, 16, 2>(s);
+  }
+  if constexpr (K == 1) {
+    if (s.tile == 312) return launch_r1_t<K, R, T, 3, 12>(s);
+    if (s.tile == 310) return launch_r1_t<K, R, T, 3, 10>(s);
+    if (s.tile == 316) return launch_r1_t<K, R, T, 3, 16>(s);
+  }
+  // defaults from the B200 sweep: fp64 constant coefficients run best with 4 rows per thread and 8
+  // warps (fewest shared-memory exchanges per point), everything else with 2 rows and 16 warps
+  if constexpr (KTraits<K>::NCA == 0 && sizeof(R) == 8) return launch_r1_t<K, R, T, 4, 8>(s);
   else return launch_r1_t<K, R, T, 2, 16>(s);
 }
 
@@ -113,7 +129,9 @@ static cudaError_t launch_r1_depth(int T, const StreamLaunch &s) {
     case 1: return launch_r1_tile<K, R, 1>(s);
     case 2: return launch_r1_tile<K, R, 2>(s);
     case 3: return launch_r1_tile<K, R, 3>(s);
-    case 4: return launch_r1_tile<K, R, 4>(s);
+    case 4:
+      if constexpr (KTraits<K>::NCA == 0) return launch_r1_tile<K, R, 4>(s);
+      else return cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
   }
 }

@@ -2,13 +2,40 @@
 #include <algorithm>
 
 #include "kernels_r4.cuh"
+#include "kernels_r4_strip.cuh"
 #include "launch.h"
 
 namespace girih {
 
-template <int K, typename R, int PY, int NW>
+template <int K, typename R, int NW>
 static cudaError_t launch_r4_t(const StreamLaunch &s) {
-  using Cfg = R4Cfg<R, PY, NW>;
+  using Cfg = R4Cfg<R, NW>;
+  const DevGrid &g = s.g;
+  R4Args<R> a;
+  a.g = g;
+  a.v = (const R *)s.in;
+  a.u = (R *)s.out;
+  a.roc2 = (const R *)s.roc2;
+  a.coef = (const R *)s.coef;
+  a.coef_stride = s.coef_stride;
+  for (int i = 0; i < 5; ++i) a.cc.v[i] = (R)s.cc[i];
+  a.zb0 = s.zb0;
+  a.ze0 = s.ze0;
+  const int ntx = (g.nx + Cfg::WX - 1) / Cfg::WX, nty = (g.ny + Cfg::H - 1) / Cfg::H;
+  int zchunk = s.zchunk;
+  if (zchunk <= 0) zchunk = std::max(1, std::min(s.ze0 - s.zb0, 32));   // measured best on B200 (kernel sweep)
+  a.zchunk = zchunk;
+  dim3 grid(ntx, nty, (s.ze0 - s.zb0 + zchunk - 1) / zchunk);
+  auto kfn = k_r4<K, R, NW>;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  if (e != cudaSuccess) return e;
+  kfn<<<grid, 32 * NW, Cfg::SMEM, s.stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <int K, typename R, int PY, int NW>
+static cudaError_t launch_r4_strip_t(const StreamLaunch &s) {
+  using Cfg = R4StripCfg<R, PY, NW>;
   const DevGrid &g = s.g;
   R4Args<R> a;
   a.g = g;
@@ -30,7 +57,7 @@ static cudaError_t launch_r4_t(const StreamLaunch &s) {
   }
   a.zchunk = zchunk;
   dim3 grid(ntx, nty, (s.ze0 - s.zb0 + zchunk - 1) / zchunk);
-  auto kfn = k_r4<K, R, PY, NW>;
+  auto kfn = k_r4_strip<K, R, PY, NW>;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
   if (e != cudaSuccess) return e;
   kfn<<<grid, 32 * NW, Cfg::SMEM, s.stream>>>(a);
@@ -38,8 +65,16 @@ static cudaError_t launch_r4_t(const StreamLaunch &s) {
 }
 
 cudaError_t launch_r4(int kernel, int es, const StreamLaunch &s) {
-  if (kernel == 0) return es == 8 ? launch_r4_t<0, double, 2, 8>(s) : launch_r4_t<0, float, 2, 8>(s);
-  if (kernel == 4) return es == 8 ? launch_r4_t<4, double, 2, 8>(s) : launch_r4_t<4, float, 2, 8>(s);
+  // tile option = warps (rows) per CTA
+  if (kernel == 0) {
+    if (s.tile == 16) return es == 8 ? launch_r4_t<0, double, 16>(s) : launch_r4_t<0, float, 16>(s);
+    return es == 8 ? launch_r4_t<0, double, 8>(s) : launch_r4_t<0, float, 8>(s);
+  }
+  if (kernel == 4) {
+    if (s.tile == 16) return es == 8 ? launch_r4_t<4, double, 16>(s) : launch_r4_t<4, float, 16>(s);
+    if (s.tile == 8) return es == 8 ? launch_r4_t<4, double, 8>(s) : launch_r4_t<4, float, 8>(s);
+    return es == 8 ? launch_r4_strip_t<4, double, 2, 8>(s) : launch_r4_strip_t<4, float, 2, 8>(s);
+  }
   return cudaErrorInvalidValue;
 }
 

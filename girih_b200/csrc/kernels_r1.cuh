@@ -75,7 +75,7 @@ template <int I, int N, typename F> __device__ __forceinline__ void static_for(F
   }
 }
 
-template <int K, typename R, int T, int PY, int NW>
+template <int K, typename R, int T, int PY, int NW, int DBG = 0>
 __global__ void __launch_bounds__(32 * NW, R1Cfg<R, T, PY, NW>::MINB)
 k_r1(const R1Args<R> a) {
   using Cfg = R1Cfg<R, T, PY, NW>;
@@ -197,8 +197,10 @@ k_r1(const R1Args<R> a) {
     }
 
     // publish the first/last row of the level-0 plane for next iteration's level-1 update
-    st128<R>(edge_ptr(0, cur, warp, 0) + lane * VX, S[0][iF][0]);
-    st128<R>(edge_ptr(0, cur, warp, 1) + lane * VX, S[0][iF][PY - 1]);
+    if constexpr (!(DBG & 2)) {
+      st128<R>(edge_ptr(0, cur, warp, 0) + lane * VX, S[0][iF][0]);
+      st128<R>(edge_ptr(0, cur, warp, 1) + lane * VX, S[0][iF][PY - 1]);
+    }
 
     R Ofin[PY][VX];
     static_for<0, T>([&](auto level_tag) {
@@ -213,8 +215,13 @@ k_r1(const R1Args<R> a) {
       R up[VX], dn[VX];
       {
         const int wu = (warp > 0) ? warp - 1 : 0, wd = (warp < NW - 1) ? warp + 1 : NW - 1;
-        ld128s<R>(edge_ptr(l, cur ^ 1, wu, 1) + lane * VX, up);
-        ld128s<R>(edge_ptr(l, cur ^ 1, wd, 0) + lane * VX, dn);
+        if constexpr (DBG & 2) {   // experiment: no shared-memory exchange (results invalid)
+#pragma unroll
+          for (int e = 0; e < VX; ++e) { up[e] = Cp[0][e]; dn[e] = Cp[PY - 1][e]; }
+        } else {
+          ld128s<R>(edge_ptr(l, cur ^ 1, wu, 1) + lane * VX, up);
+          ld128s<R>(edge_ptr(l, cur ^ 1, wd, 0) + lane * VX, dn);
+        }
       }
 
       auto stage = [&](R (&O)[PY][VX]) {
@@ -232,8 +239,8 @@ k_r1(const R1Args<R> a) {
             if (ok) ld128<R>(cp + (long long)m * a.coef_stride, cf[m]);
           }
         }
-        const R left = __shfl_up_sync(0xffffffffu, Cp[j][VX - 1], 1);
-        const R right = __shfl_down_sync(0xffffffffu, Cp[j][0], 1);
+        const R left = (DBG & 1) ? Cp[j][0] : __shfl_up_sync(0xffffffffu, Cp[j][VX - 1], 1);
+        const R right = (DBG & 1) ? Cp[j][VX - 1] : __shfl_down_sync(0xffffffffu, Cp[j][0], 1);
 #pragma unroll
         for (int e = 0; e < VX; ++e) {
           RegNb1<R> n;
@@ -263,7 +270,7 @@ k_r1(const R1Args<R> a) {
 #pragma unroll
             for (int e = 0; e < VX; ++e) O[j][e] = ((upd >> (j * VX + e)) & 1u) ? O[j][e] : Cp[j][e];
         }
-        if constexpr (l + 1 < T) {
+        if constexpr (l + 1 < T && !(DBG & 2)) {
           st128<R>(edge_ptr(l + 1, cur, warp, 0) + lane * VX, O[0]);
           st128<R>(edge_ptr(l + 1, cur, warp, 1) + lane * VX, O[PY - 1]);
         }
@@ -291,7 +298,7 @@ k_r1(const R1Args<R> a) {
         }
       }
     }
-    __syncthreads();
+    if constexpr (!(DBG & 2)) __syncthreads();
   };
 
   // planes zin-T .. zin-1 are produced in iteration `it`; the version is chosen per iteration

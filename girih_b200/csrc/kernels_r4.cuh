@@ -2,15 +2,17 @@
 // slot 0 (constant coefficients, 2nd order in time: reads v, u, roc2, writes u) and slot 4
 // (13 per-point axis-symmetric coefficient arrays, 1st order in time).
 //
-// Schedule (one CTA = NW warps, tile WX x (NW*PY), marching along z):
+// Schedule (one CTA = NW warps, one row per warp: tile WX x NW, marching along z):
 //   * a lane owns VX = 16 B / sizeof(Real) consecutive x points: 128-bit coalesced global access
-//   * the z column (planes z-4 .. z+4 of the thread's own points) lives in registers and is
-//     rotated once per plane; each plane of v is read from HBM exactly once per tile
+//   * the z column lives in a ring of RB = 10 register vectors (planes z-4 .. z+4 plus the plane
+//     z+5 that is still in flight).  The z loop is unrolled RB times so the ring rotates by renaming,
+//     without register moves; each plane of v is read from HBM exactly once per tile
 //   * the centre plane z is staged in shared memory together with its 4-wide x/y halo strips
-//     (double buffered, ONE __syncthreads per plane); x and y neighbours are then read back as
-//     128-bit row/column windows that are shared by the VX x PY points of a thread
-//   * u(old), roc2 and the per-point coefficients are touched at the thread's own points only,
-//     so they stream straight from HBM into registers
+//     (double buffered, ONE __syncthreads per plane); x and y neighbours are read back as 128-bit
+//     row/column windows
+//   * halo strips, u(old) and roc2 of the NEXT plane are fetched one iteration ahead into registers
+//   * per-point coefficients (slot 4) are touched at the thread's own points only and stream
+//     straight from HBM into registers
 // No temporal fusion here: with r = 4 the overlapped tile of a fused sweep wastes more than half
 // of an SM-sized tile (halo 2*T*4 per axis) and slot 0 would need two extra arrays because its
 // update reads the level it overwrites.  DESIGN.md, "r = 4 operators".
@@ -31,12 +33,13 @@ template <typename R> struct R4Args {
   int zb0, ze0, zchunk;
 };
 
-template <typename R, int PY, int NW> struct R4Cfg {
+template <typename R, int NW> struct R4Cfg {
   static constexpr int RAD = 4;
   static constexpr int VX = Vec<R>::N;
   static constexpr int WX = 32 * VX;
-  static constexpr int H = NW * PY;
+  static constexpr int H = NW;
   static constexpr int NT = 32 * NW;
+  static constexpr int RB = 10;
   static constexpr int SP = WX + 2 * RAD;        // shared row pitch (elements), 16-byte multiple
   static constexpr int SROWS = H + 2 * RAD;
   static constexpr int HXV = RAD / VX;           // halo vectors per row side
@@ -46,27 +49,31 @@ template <typename R, int PY, int NW> struct R4Cfg {
   static_assert(RAD % VX == 0, "halo must be whole vectors");
 };
 
-template <typename R, int PY> struct RegNb4 {
+// neighbour accessor: z from the register ring, x from the row window, y from the column window
+template <typename R, int PH> struct RegNb4 {
   static constexpr int VX = Vec<R>::N;
-  const R (*zc)[PY][VX];     // zc[0..8] = planes z-4 .. z+4 at my points
-  const R *xr;               // row window: x-4 .. x+VX+3 of row j
-  const R (*yc)[VX];         // column window: rows y0-4 .. y0+PY+3
-  int j, e;
+  const R (*ring)[VX];       // ring[(PH + i) % 10] = plane z-4+i
+  const R *xr;               // x-4 .. x+VX+3
+  const R (*yc)[VX];         // rows y-4 .. y+4 (index 4 = my row)
+  int e;
   template <int DX, int DY, int DZ> __device__ __forceinline__ R at() const {
-    if constexpr (DZ != 0) return zc[4 + DZ][j][e];
+    if constexpr (DZ != 0) return ring[(PH + 4 + DZ) % 10][e];
     else if constexpr (DX != 0) return xr[4 + e + DX];
-    else if constexpr (DY != 0) return yc[4 + j + DY][e];
-    else return zc[4][j][e];
+    else if constexpr (DY != 0) return yc[4 + DY][e];
+    else return ring[(PH + 4) % 10][e];
   }
 };
 
-template <int K, typename R, int PY, int NW>
+template <int I> struct R4Phase { static constexpr int value = I; };
+
+template <int K, typename R, int NW>
 __global__ void __launch_bounds__(32 * NW)
 k_r4(const R4Args<R> a) {
-  using Cfg = R4Cfg<R, PY, NW>;
-  constexpr int RAD = Cfg::RAD, VX = Cfg::VX, WX = Cfg::WX, H = Cfg::H, NT = Cfg::NT;
+  using Cfg = R4Cfg<R, NW>;
+  constexpr int RAD = Cfg::RAD, VX = Cfg::VX, WX = Cfg::WX, H = Cfg::H, NT = Cfg::NT, RB = Cfg::RB;
   constexpr int SP = Cfg::SP, SROWS = Cfg::SROWS, HXV = Cfg::HXV, NHV = Cfg::NHV, HPT = Cfg::HPT;
   constexpr int NCA = KTraits<K>::NCA;
+  constexpr bool TO2 = KTraits<K>::TO == 2;
   static_assert(KTraits<K>::R == 4, "radius-4 operators only");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -75,21 +82,16 @@ k_r4(const R4Args<R> a) {
   const DevGrid &g = a.g;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int x0t = g.X0 + (int)blockIdx.x * WX, y0t = g.Y0 + (int)blockIdx.y * H;
-  const int x = x0t + lane * VX, y0 = y0t + warp * PY;
+  const int x = x0t + lane * VX, y = y0t + warp;
   const int zb = a.zb0 + (int)blockIdx.z * a.zchunk;
   const int ze = min(zb + a.zchunk, a.ze0);
 
-  const bool x_alloc = (x + VX <= g.px);
-  bool row_alloc[PY];
-  unsigned interior_xy = 0;
+  const bool ok = (x + VX <= g.px) && (y < g.ny_dev);     // my vector may be loaded
+  unsigned inter = 0;                                      // bit e: point is interior in x and y
 #pragma unroll
-  for (int j = 0; j < PY; ++j) {
-    row_alloc[j] = x_alloc && (y0 + j < g.ny_dev);
-#pragma unroll
-    for (int e = 0; e < VX; ++e)
-      if ((x + e < g.X0 + g.nx) && (y0 + j < g.Y0 + g.ny)) interior_xy |= 1u << (j * VX + e);
-  }
-  const long long row0 = (long long)y0 * g.px + x;
+  for (int e = 0; e < VX; ++e)
+    if ((x + e < g.X0 + g.nx) && (y < g.Y0 + g.ny)) inter |= 1u << e;
+  const long long off = (long long)y * g.px + x;
 
   // my share of the halo strips of a plane: top/bottom 4 rows over the tile width, left/right 4
   // columns over the tile height (a star stencil never reads the corners)
@@ -117,155 +119,129 @@ k_r4(const R4Args<R> a) {
     h_ok[h] = (item < NHV) && (gx >= 0) && (gx + VX <= g.px) && (gy >= 0) && (gy < g.ny_dev);
   }
 
-  auto load_rows = [&](const R *base, int z, R (&dst)[PY][VX], bool coherent = false) {
-    const bool zok = (z >= 0) && (z < g.nz_dev);
-    const R *p = base + (long long)z * g.pxy + row0;
+  R ring[RB][VX];           // ring[(ph + i) % RB] = plane z-4+i (i = 0..8), (ph + 9) % RB in flight
+  R hal[2][HPT][VX];        // [parity] halo vectors of the plane staged in that parity
+  R uo[2][VX], rc[2][VX];   // [parity] u(old) and roc2 of that plane (slot 0)
 #pragma unroll
-    for (int j = 0; j < PY; ++j) {
-      if (zok && row_alloc[j]) {
-        if (coherent) ld128g<R>(p + (long long)j * g.px, dst[j]);
-        else ld128<R>(p + (long long)j * g.px, dst[j]);
-      }
-      else {
+  for (int i = 0; i < RB; ++i)
 #pragma unroll
-        for (int e = 0; e < VX; ++e) dst[j][e] = (R)0;
-      }
-    }
-  };
-  auto load_halo = [&](int z, R (&dst)[HPT][VX]) {
-    const bool zok = (z >= 0) && (z < g.nz_dev);
-    const R *p = a.v + (long long)z * g.pxy;
+    for (int e = 0; e < VX; ++e) ring[i][e] = (R)0;
 #pragma unroll
-    for (int h = 0; h < HPT; ++h) {
-      if (zok && h_ok[h]) ld128<R>(p + hg_off[h], dst[h]);
-      else {
+  for (int b = 0; b < 2; ++b) {
 #pragma unroll
-        for (int e = 0; e < VX; ++e) dst[h][e] = (R)0;
-      }
-    }
-  };
-
-  // z column: zc[i] = plane z-4+i.  Primed so that after the first rotation zc[0..7] = zb-4 .. zb+3
-  R zc[9][PY][VX];
+    for (int h = 0; h < HPT; ++h)
 #pragma unroll
-  for (int j = 0; j < PY; ++j)
+      for (int e = 0; e < VX; ++e) hal[b][h][e] = (R)0;
 #pragma unroll
-    for (int e = 0; e < VX; ++e) zc[0][j][e] = (R)0;
-#pragma unroll
-  for (int i = 1; i < 9; ++i) load_rows(a.v, zb - 5 + i, zc[i]);
-  R vnext[PY][VX], hnext[HPT][VX];
-  load_rows(a.v, zb + 4, vnext);
-  load_halo(zb, hnext);
-  R uo_n[PY][VX], rc_n[PY][VX];
-  if constexpr (KTraits<K>::TO == 2) {
-    load_rows(a.u, zb, uo_n, true);
-    load_rows(a.roc2, zb, rc_n);
+    for (int e = 0; e < VX; ++e) { uo[b][e] = (R)0; rc[b][e] = (R)0; }
   }
 
-  for (int z = zb; z < ze; ++z) {
-    const int cur = (z - zb) & 1;
-    R *s = sm + (size_t)cur * SROWS * SP;
-
-    // rotate the z column, take the prefetched plane z+4, start the next prefetches
+  auto fetch_v = [&](int z, R (&dst)[VX]) {
+    if (ok && z >= 0 && z < g.nz_dev) ld128<R>(a.v + off + (long long)z * g.pxy, dst);
+  };
+  auto fetch_side = [&](int z, R (&hd)[HPT][VX], R (&ud)[VX], R (&rd)[VX]) {
+    if (z >= 0 && z < g.nz_dev) {
+      const R *p = a.v + (long long)z * g.pxy;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < PY; ++j)
-#pragma unroll
-        for (int e = 0; e < VX; ++e) zc[i][j][e] = zc[i + 1][j][e];
-#pragma unroll
-    for (int j = 0; j < PY; ++j)
-#pragma unroll
-      for (int e = 0; e < VX; ++e) zc[8][j][e] = vnext[j][e];
-    R hcur[HPT][VX];
-#pragma unroll
-    for (int h = 0; h < HPT; ++h)
-#pragma unroll
-      for (int e = 0; e < VX; ++e) hcur[h][e] = hnext[h][e];
-    R uo[PY][VX], rc[PY][VX];
-    if constexpr (KTraits<K>::TO == 2) {
-#pragma unroll
-      for (int j = 0; j < PY; ++j)
-#pragma unroll
-        for (int e = 0; e < VX; ++e) { uo[j][e] = uo_n[j][e]; rc[j][e] = rc_n[j][e]; }
-    }
-    if (z + 1 < ze) {
-      load_rows(a.v, z + 5, vnext);
-      load_halo(z + 1, hnext);
-      if constexpr (KTraits<K>::TO == 2) {
-        load_rows(a.u, z + 1, uo_n, true);
-        load_rows(a.roc2, z + 1, rc_n);
+      for (int h = 0; h < HPT; ++h)
+        if (h_ok[h]) ld128<R>(p + hg_off[h], hd[h]);
+      if constexpr (TO2) {
+        if (ok) {
+          ld128g<R>(a.u + off + (long long)z * g.pxy, ud);       // same kernel overwrites u: coherent load
+          ld128<R>(a.roc2 + off + (long long)z * g.pxy, rd);
+        }
       }
     }
+  };
 
-    // stage plane z: my own points from the register column, my share of the halo strips
+  // prologue: planes zb-4 .. zb+4 of my column, side data of plane zb
 #pragma unroll
-    for (int j = 0; j < PY; ++j)
-      st128<R>(s + (RAD + warp * PY + j) * SP + RAD + lane * VX, zc[4][j]);
+  for (int i = 0; i < 9; ++i) fetch_v(zb - 4 + i, ring[i]);
+  fetch_side(zb, hal[0], uo[0], rc[0]);
+
+  auto body = [&](auto phase_tag, const int z) {
+    constexpr int PH = decltype(phase_tag)::value;
+    constexpr int PAR = PH & 1;
+    R *s = sm + (size_t)PAR * SROWS * SP;
+    // keep the column one plane ahead of what the next iteration needs, side data one plane ahead
+    if (z + 1 < ze) {
+      fetch_v(z + 5, ring[(PH + 9) % RB]);
+      fetch_side(z + 1, hal[PAR ^ 1], uo[PAR ^ 1], rc[PAR ^ 1]);
+    }
+    // stage plane z: my own points from the register ring, my share of the halo strips
+    st128<R>(s + (RAD + warp) * SP + RAD + lane * VX, ring[(PH + 4) % RB]);
 #pragma unroll
     for (int h = 0; h < HPT; ++h)
-      if (tid + h * NT < NHV) st128<R>(s + hs_off[h], hcur[h]);
+      if (tid + h * NT < NHV) st128<R>(s + hs_off[h], hal[PAR][h]);
     __syncthreads();
 
-    // column window shared by my PY rows: rows y0-4 .. y0+PY+3 at my VX columns
-    R yc[PY + 2 * RAD][VX];
+    // windows around my points: rows y-4 .. y+4 at my columns, columns x-4 .. x+VX+3 of my row
+    R yc[2 * RAD + 1][VX];
 #pragma unroll
-    for (int q = 0; q < PY + 2 * RAD; ++q) {
-      if (q >= RAD && q < RAD + PY) {
+    for (int q = 0; q < 2 * RAD + 1; ++q)
+      if (q != RAD) ld128s<R>(s + (warp + q) * SP + RAD + lane * VX, yc[q]);
+    R xr[VX + 2 * RAD];
 #pragma unroll
-        for (int e = 0; e < VX; ++e) yc[q][e] = zc[4][q - RAD][e];
+    for (int q = 0; q < (VX + 2 * RAD) / VX; ++q) {
+      R t[VX];
+      if (q * VX == RAD) {
+#pragma unroll
+        for (int e = 0; e < VX; ++e) t[e] = ring[(PH + 4) % RB][e];
       } else {
-        ld128s<R>(s + (warp * PY + q) * SP + RAD + lane * VX, yc[q]);
+        ld128s<R>(s + (RAD + warp) * SP + lane * VX + q * VX, t);
+      }
+#pragma unroll
+      for (int e = 0; e < VX; ++e) xr[q * VX + e] = t[e];
+    }
+    R cfr[NCA > 0 ? NCA : 1][VX];
+    if constexpr (NCA > 0) {
+      const R *cp = a.coef + off + (long long)z * g.pxy;
+#pragma unroll
+      for (int m = 0; m < NCA; ++m) {
+#pragma unroll
+        for (int e = 0; e < VX; ++e) cfr[m][e] = (R)0;
+        if (ok) ld128<R>(cp + (long long)m * a.coef_stride, cfr[m]);
       }
     }
-
-    R *outp = a.u + (long long)z * g.pxy + row0;
+    R o[VX];
 #pragma unroll
-    for (int j = 0; j < PY; ++j) {
-      // row window x-4 .. x+VX+3
-      R xr[VX + 2 * RAD];
-#pragma unroll
-      for (int q = 0; q < (VX + 2 * RAD) / VX; ++q) {
-        R t[VX];
-        ld128s<R>(s + (RAD + warp * PY + j) * SP + lane * VX + q * VX, t);
-#pragma unroll
-        for (int e = 0; e < VX; ++e) xr[q * VX + e] = t[e];
-      }
-      R cfr[NCA > 0 ? NCA : 1][VX];
+    for (int e = 0; e < VX; ++e) {
+      RegNb4<R, PH> n{ring, xr, yc, e};
       if constexpr (NCA > 0) {
-        const R *cp = a.coef + (long long)z * g.pxy + row0 + (long long)j * g.px;
+        RegCoef<R, NCA> cfp;
 #pragma unroll
-        for (int m = 0; m < NCA; ++m) {
-          if (row_alloc[j]) ld128<R>(cp + (long long)m * a.coef_stride, cfr[m]);
-          else {
-#pragma unroll
-            for (int e = 0; e < VX; ++e) cfr[m][e] = (R)0;
-          }
-        }
-      }
-      R o[VX];
-#pragma unroll
-      for (int e = 0; e < VX; ++e) {
-        RegNb4<R, PY> n{zc, xr, yc, j, e};
-        if constexpr (NCA > 0) {
-          RegCoef<R, NCA> cfp;
-#pragma unroll
-          for (int m = 0; m < NCA; ++m) cfp.v[m] = cfr[m][e];
-          o[e] = StencilExpr<K>::template eval<R>(n, cfp, (R)0, (R)0);
-        } else {
-          o[e] = StencilExpr<K>::template eval<R>(n, a.cc, uo[j][e], rc[j][e]);
-        }
-      }
-      const unsigned m = (interior_xy >> (j * VX)) & ((1u << VX) - 1u);
-      if (m == (1u << VX) - 1u) {
-        st128<R>(outp + (long long)j * g.px, o);
-      } else if (m != 0u) {
-#pragma unroll
-        for (int e = 0; e < VX; ++e)
-          if ((m >> e) & 1u) outp[(long long)j * g.px + e] = o[e];
+        for (int m = 0; m < NCA; ++m) cfp.v[m] = cfr[m][e];
+        o[e] = StencilExpr<K>::template eval<R>(n, cfp, (R)0, (R)0);
+      } else {
+        o[e] = StencilExpr<K>::template eval<R>(n, a.cc, uo[PAR][e], rc[PAR][e]);
       }
     }
+    R *outp = a.u + off + (long long)z * g.pxy;
+    if (inter == (1u << VX) - 1u) {
+      st128<R>(outp, o);
+    } else if (inter != 0u) {
+#pragma unroll
+      for (int e = 0; e < VX; ++e)
+        if ((inter >> e) & 1u) outp[e] = o[e];
+    }
+  };
+
+  int z = zb;
+  for (; z + RB <= ze; z += RB) {
+    body(R4Phase<0>{}, z);     body(R4Phase<1>{}, z + 1); body(R4Phase<2>{}, z + 2);
+    body(R4Phase<3>{}, z + 3); body(R4Phase<4>{}, z + 4); body(R4Phase<5>{}, z + 5);
+    body(R4Phase<6>{}, z + 6); body(R4Phase<7>{}, z + 7); body(R4Phase<8>{}, z + 8);
+    body(R4Phase<9>{}, z + 9);
   }
+  if (z < ze) { body(R4Phase<0>{}, z); ++z; }
+  if (z < ze) { body(R4Phase<1>{}, z); ++z; }
+  if (z < ze) { body(R4Phase<2>{}, z); ++z; }
+  if (z < ze) { body(R4Phase<3>{}, z); ++z; }
+  if (z < ze) { body(R4Phase<4>{}, z); ++z; }
+  if (z < ze) { body(R4Phase<5>{}, z); ++z; }
+  if (z < ze) { body(R4Phase<6>{}, z); ++z; }
+  if (z < ze) { body(R4Phase<7>{}, z); ++z; }
+  if (z < ze) { body(R4Phase<8>{}, z); }
 }
 
 }  // namespace girih

@@ -40,6 +40,7 @@ def test_kernel_table_matches_reference_list():
     assert not G.kernel_info(6).gpu_supported
     # algorithmic words per LUP, SURVEY.md 8(d)
     assert [G.kernel_info(k).words_per_lup for k in (0, 1, 2, 3, 4, 5)] == [4, 2, 4, 6, 15, 9]
+    assert [G.kernel_info(k).max_tfuse for k in (0, 1, 2, 3, 4, 5, 7)] == [1, 4, 3, 3, 1, 3, 1]
 
 
 def _create(kernel, es, st, ds, rank=0, nranks=1):
