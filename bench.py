@@ -201,6 +201,7 @@ def main_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
     torch.cuda.set_device(local)
+    os.environ["NCCL_DEBUG"] = os.environ.get("GIRIH_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -339,7 +340,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tfuse", type=int, default=0)
     ap.add_argument("--ref-nz", type=int, default=512, help="z extent of the bounded CPU sample")
-    ap.add_argument("--ref-nt", type=int, default=50, help="time steps of the bounded CPU sample")
+    ap.add_argument("--ref-nt", type=int, default=500, help="time steps of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

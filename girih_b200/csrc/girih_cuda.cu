@@ -84,7 +84,7 @@ struct girih_gpu_ctx {
   // NCCL
   ncclComm_t comm = nullptr;
   // options
-  int opt_variant = 0, opt_zchunk = 0, opt_tile = 0, opt_overlap = 1;
+  int opt_variant = 0, opt_zchunk = 0, opt_tile = 0, opt_overlap = 0;
   // accounting of the last run
   double ms_compute = 0, ms_comm = 0, ms_total = 0;
   int n_kernels = 0, n_passes = 0, n_steps = 0, tfuse_used = 1;

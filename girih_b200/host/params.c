@@ -46,7 +46,7 @@ void param_default(Parameters *p) {
   p->wavefront = 1;
   p->num_wf = -1;
   p->t.shape[0] = p->t.shape[1] = p->t.shape[2] = 1;
-  p->gpu_overlap = 1;
+  p->gpu_overlap = 0;
   for (i = 0; i < 11; i++) p->g_coef[i] = (real_t)coef[i];
   reset_timers(&p->prof);
 }
@@ -105,7 +105,7 @@ void print_help(Parameters *p) {
         "  --mwd-type <int>\n       MWD variant (all variants map to the one fused GPU sweep)\n"
         "  --gpu-tfuse <int>\n       Time steps fused per HBM pass by the Diamond stepper (0 = default)\n"
         "  --gpu-variant <int>\n       0 streamed kernels (default), 1 naive kernels\n"
-        "  --gpu-overlap <bool>\n       Overlap the halo exchange with interior compute (default 1)\n"
+        "  --gpu-overlap <bool>\n       Diamond stepper: compute the slab boundaries first and overlap the deep-halo exchange\n       with the interior (default 0: one blocking exchange per fused pass measured faster)\n"
         "  --z-mpi-contig <bool>  --halo-concatenate <integer>  --thread-group-size <integer>\n"
         "  --thx/--thy/--thz/--thc <integer>  --cache-size <integer>  --wavefront <bool>\n"
         "  --num-wavefronts <int>  --use-omp-stat-sched  --threads n[:block[:stride]]\n"

@@ -167,7 +167,8 @@ int girih_gpu_scan_u1(girih_gpu_ctx *ctx, uint64_t *n_nan_inf, uint64_t *n_zero)
  *              2 fused-sweep kernel also for T = 1
  *   "zchunk"   output planes per CTA (0 = choose)
  *   "tile"     fused sweep: PY*100 + NW (rows per thread, warps per CTA); marching kernel: rows per CTA
- *   "overlap"  overlap the halo exchange of fused passes with compute (default 1) */
+ *   "overlap"  fused passes: compute the slab boundaries first and overlap the deep-halo exchange with
+ *              the interior (default 0: one exchange per pass, ordered before it, measured faster) */
 int girih_gpu_set_option(girih_gpu_ctx *ctx, const char *key, int value);
 
 const char *girih_gpu_strerror(int status);
