@@ -229,6 +229,25 @@ class GpuStepper:
         return a.value, b.value
 
 
+def plan_fused_passes(nsteps: int, tfuse: int) -> list:
+    """steps per pass that girih_gpu_run_fused executes (host-only)"""
+    n = C.c_int()
+    buf = (C.c_int * (nsteps + 4))()
+    rc = _lib.cuda().girih_plan_fused_passes(nsteps, tfuse, buf, nsteps + 4, C.byref(n))
+    if rc:
+        raise GirihError(rc, "girih_plan_fused_passes")
+    return list(buf[:n.value])
+
+
+def plan_halo_exchange(nz: int, depth: int, rank: int, nranks: int) -> dict:
+    """first local plane of the send/recv blocks of one z exchange (host-only)"""
+    v = [C.c_int() for _ in range(4)]
+    rc = _lib.cuda().girih_plan_halo_exchange(nz, depth, rank, nranks, *[C.byref(x) for x in v])
+    if rc:
+        raise GirihError(rc, "girih_plan_halo_exchange")
+    return dict(zip(("send_down", "recv_down", "send_up", "recv_up"), (x.value for x in v)))
+
+
 def run_reference_cli(dtype, args, timeout=3600, env=None):
     """Run this repo's own mwd_kernel executable (build/ = fp32, build_dp/ = fp64); returns
     (returncode, stdout, stderr)."""

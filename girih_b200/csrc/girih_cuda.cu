@@ -347,6 +347,9 @@ extern "C" int girih_gpu_comm_init(girih_gpu_ctx *c, const void *id, size_t len)
   return GIRIH_OK;
 }
 
+extern "C" int girih_plan_halo_exchange(int nz, int depth, int rank, int nranks, int *send_down, int *recv_down,
+                                        int *send_up, int *recv_up);
+
 // Exchange `depth` planes of `arr` with both z neighbours on the comm stream: my top `depth`
 // interior planes go to the upper neighbour's lower halo and vice versa (geometry of
 // src/mpi_utils.c:173-200 generalised from r to depth = T*r planes).  Planes are contiguous,
@@ -359,14 +362,17 @@ static int exchange_z(girih_gpu_ctx *c, void *arr, int depth, cudaStream_t s) {
   const size_t count = (size_t)depth * plane_b;
   char *base = (char *)arr;
   const int up = c->rank + 1, dn = c->rank - 1;
+  int sd, rd, su, ru;
+  if (girih_plan_halo_exchange(g.nz, depth, c->rank, c->nranks, &sd, &rd, &su, &ru) != GIRIH_OK)
+    return fail(c, GIRIH_ERR_ARG, "halo depth %d does not fit a slab of %d planes", depth, g.nz);
   NC(nccl_dyn()->GroupStart());
   if (dn >= 0) {
-    NC(nccl_dyn()->Send(base + (size_t)g.Z0 * plane_b, count, ncclChar, dn, c->comm, s));
-    NC(nccl_dyn()->Recv(base + (size_t)(g.Z0 - depth) * plane_b, count, ncclChar, dn, c->comm, s));
+    NC(nccl_dyn()->Send(base + (size_t)(g.Z0 + sd) * plane_b, count, ncclChar, dn, c->comm, s));
+    NC(nccl_dyn()->Recv(base + (size_t)(g.Z0 + rd) * plane_b, count, ncclChar, dn, c->comm, s));
   }
   if (up < c->nranks) {
-    NC(nccl_dyn()->Send(base + (size_t)(g.Z0 + g.nz - depth) * plane_b, count, ncclChar, up, c->comm, s));
-    NC(nccl_dyn()->Recv(base + (size_t)(g.Z0 + g.nz) * plane_b, count, ncclChar, up, c->comm, s));
+    NC(nccl_dyn()->Send(base + (size_t)(g.Z0 + su) * plane_b, count, ncclChar, up, c->comm, s));
+    NC(nccl_dyn()->Recv(base + (size_t)(g.Z0 + ru) * plane_b, count, ncclChar, up, c->comm, s));
   }
   NC(nccl_dyn()->GroupEnd());
   return GIRIH_OK;
@@ -559,6 +565,55 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
   return GIRIH_OK;
 }
 
+// The pass schedule of the fused stepper.  All but the last step are fused; the last one is a single
+// step so that BOTH arrays end up holding the levels the reference leaves (newest and newest-1).
+// Every pass moves the newest level to the other array, and level n must end in U1 when n is odd: the
+// number of passes that cover the first nsteps-1 steps must have the parity of nsteps-1.
+static void plan_passes(int nsteps, int T, std::vector<int> &sizes) {
+  sizes.clear();
+  if (nsteps <= 0) return;
+  if (T < 1) T = 1;
+  int n1 = nsteps - 1;
+  while (n1 >= T) { sizes.push_back(T); n1 -= T; }
+  if (n1 > 0) sizes.push_back(n1);
+  if (((int)sizes.size() - (nsteps - 1)) % 2 != 0) {
+    // some pass has >= 2 steps here (otherwise the count equals the step count): split it
+    for (size_t i = sizes.size(); i-- > 0;)
+      if (sizes[i] >= 2) {
+        const int a1 = sizes[i] / 2, a2 = sizes[i] - a1;
+        sizes[i] = a2;
+        sizes.insert(sizes.begin() + (long)i + 1, a1);
+        break;
+      }
+  }
+  sizes.push_back(1);
+}
+
+extern "C" int girih_plan_fused_passes(int nsteps, int tfuse, int *sizes, int max_sizes, int *n_sizes) {
+  if (nsteps < 0 || tfuse < 1 || !n_sizes) return GIRIH_ERR_ARG;
+  std::vector<int> v;
+  plan_passes(nsteps, tfuse, v);
+  *n_sizes = (int)v.size();
+  if (sizes) {
+    if ((int)v.size() > max_sizes) return GIRIH_ERR_ARG;
+    for (size_t i = 0; i < v.size(); ++i) sizes[i] = v[i];
+  }
+  return GIRIH_OK;
+}
+
+// Plane ranges of one z-halo exchange of `depth` planes, in LOCAL plane coordinates (0 = first interior
+// plane of the slab, nz = number of interior planes).  A negative start means "no neighbour on that side".
+extern "C" int girih_plan_halo_exchange(int nz, int depth, int rank, int nranks, int *send_down, int *recv_down,
+                                        int *send_up, int *recv_up) {
+  if (nz < 1 || depth < 1 || depth > nz || nranks < 1 || rank < 0 || rank >= nranks) return GIRIH_ERR_ARG;
+  const bool dn = rank > 0, up = rank + 1 < nranks;
+  if (send_down) *send_down = dn ? 0 : -1;               // my lowest `depth` interior planes
+  if (recv_down) *recv_down = dn ? -depth : -1 - depth;   // land below my interior
+  if (send_up) *send_up = up ? nz - depth : -1;          // my highest `depth` interior planes
+  if (recv_up) *recv_up = up ? nz : -1;                  // land above my interior
+  return GIRIH_OK;
+}
+
 static int finish_halos(girih_gpu_ctx *c) {
   // leave both arrays with exchanged r-deep halos, as the reference's steppers do
   // (src/kernels/nb_naive_ts.c:192,198)
@@ -593,27 +648,8 @@ extern "C" int girih_gpu_run_fused(girih_gpu_ctx *c, int nsteps, int tfuse) {
   int rc;
   if ((rc = begin_run(c))) return rc;
   if ((rc = exchange_static(c))) return rc;
-  // All but the last step are fused; the last one is a single step so that BOTH arrays end up
-  // holding the levels the reference leaves (newest and newest-1).  Every pass moves the newest
-  // level to the other array, and level n must end in U1 when n is odd: the number of passes that
-  // cover the first nsteps-1 steps must have the parity of nsteps-1.
   std::vector<int> sizes;
-  if (nsteps > 0) {
-    int n1 = nsteps - 1;
-    while (n1 >= T) { sizes.push_back(T); n1 -= T; }
-    if (n1 > 0) sizes.push_back(n1);
-    if (((int)sizes.size() - (nsteps - 1)) % 2 != 0) {
-      // some pass has >= 2 steps here (otherwise the count equals the step count): split it
-      for (size_t i = sizes.size(); i-- > 0;)
-        if (sizes[i] >= 2) {
-          const int a1 = sizes[i] / 2, a2 = sizes[i] - a1;
-          sizes[i] = a2;
-          sizes.insert(sizes.begin() + (long)i + 1, a1);
-          break;
-        }
-    }
-    sizes.push_back(1);
-  }
+  plan_passes(nsteps, T, sizes);
   int cur = 1;
   if ((rc = run_passes(c, sizes, cur, c->opt_overlap != 0))) return rc;
   if (nsteps > 0 && cur != ((nsteps % 2 == 1) ? 0 : 1))

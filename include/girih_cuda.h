@@ -137,6 +137,17 @@ int girih_gpu_upload_fields(girih_gpu_ctx *ctx, const void *U1, const void *U2);
 int girih_gpu_run_single(girih_gpu_ctx *ctx, int nsteps, int overlap);
 int girih_gpu_run_fused(girih_gpu_ctx *ctx, int nsteps, int tfuse);
 
+/* Host-only planning helpers (no device needed).  They return exactly what girih_gpu_run_fused and the
+ * halo exchange execute, so the multi-rank logic can be exercised without GPUs:
+ *   girih_plan_fused_passes   steps per pass for nsteps steps at depth tfuse (the last entry is the
+ *                             single step that leaves U1/U2 as the reference does); sizes may be NULL
+ *   girih_plan_halo_exchange  first plane of the four `depth`-plane blocks of one z exchange, in local
+ *                             plane coordinates (0 = first interior plane); -1 / <-depth = no neighbour.
+ *                             Geometry of src/mpi_utils.c:173-200 with depth = T*r instead of r. */
+int girih_plan_fused_passes(int nsteps, int tfuse, int *sizes, int max_sizes, int *n_sizes);
+int girih_plan_halo_exchange(int nz, int depth, int rank, int nranks, int *send_down, int *recv_down,
+                             int *send_up, int *recv_up);
+
 /* One application of the operator over the box [xb,xe) x [yb,ye) x [zb,ze) in HOST index space
  * (the spt_blk_func_t contract, src/kernels/stencils_spt_blk.ic:19-48): dst=1 writes U1 from U2,
  * dst=2 writes U2 from U1. */
