@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "girih_cuda.h")).read()
-    declared = set(re.findall(r"\b(girih_(?:gpu|kernel)_\w+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(girih_(?:gpu|kernel|plan)_\w+)\s*\(", hdr))
     assert declared == set(L.ABI_SYMBOLS)
     lib = L.cuda()
     for s in declared:
