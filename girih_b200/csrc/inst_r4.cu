@@ -64,11 +64,42 @@ static cudaError_t launch_r4_strip_t(const StreamLaunch &s) {
   return cudaGetLastError();
 }
 
+template <int K, typename R, int NW>
+static cudaError_t launch_r4_async_t(const StreamLaunch &s) {
+  using Cfg = R4Cfg<R, NW>;
+  using ACfg = R4ACfg<R, NW>;
+  const DevGrid &g = s.g;
+  R4Args<R> a;
+  a.g = g;
+  a.v = (const R *)s.in;
+  a.u = (R *)s.out;
+  a.roc2 = (const R *)s.roc2;
+  a.coef = (const R *)s.coef;
+  a.coef_stride = s.coef_stride;
+  for (int i = 0; i < 5; ++i) a.cc.v[i] = (R)s.cc[i];
+  a.zb0 = s.zb0;
+  a.ze0 = s.ze0;
+  const int ntx = (g.nx + Cfg::WX - 1) / Cfg::WX, nty = (g.ny + Cfg::H - 1) / Cfg::H;
+  int zchunk = s.zchunk;
+  if (zchunk <= 0) zchunk = std::max(1, std::min(s.ze0 - s.zb0, 64));
+  a.zchunk = zchunk;
+  dim3 grid(ntx, nty, (s.ze0 - s.zb0 + zchunk - 1) / zchunk);
+  auto kfn = k_r4_async<K, R, NW>;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACfg::SMEM);
+  if (e != cudaSuccess) return e;
+  kfn<<<grid, 32 * NW, ACfg::SMEM, s.stream>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_r4(int kernel, int es, const StreamLaunch &s) {
   // tile option = warps (rows) per CTA
+  // tile option: 8 / 16 = ring variant with that many rows per CTA, 116 = cp.async variant with 16 rows;
+  // default = cp.async variant, 8 rows per CTA (measured fastest: 88-90% of the HBM peak at 512^3)
   if (kernel == 0) {
+    if (s.tile == 8) return es == 8 ? launch_r4_t<0, double, 8>(s) : launch_r4_t<0, float, 8>(s);
     if (s.tile == 16) return es == 8 ? launch_r4_t<0, double, 16>(s) : launch_r4_t<0, float, 16>(s);
-    return es == 8 ? launch_r4_t<0, double, 8>(s) : launch_r4_t<0, float, 8>(s);
+    if (s.tile == 116) return es == 8 ? launch_r4_async_t<0, double, 16>(s) : launch_r4_async_t<0, float, 16>(s);
+    return es == 8 ? launch_r4_async_t<0, double, 8>(s) : launch_r4_async_t<0, float, 8>(s);
   }
   if (kernel == 4) {
     if (s.tile == 16) return es == 8 ? launch_r4_t<4, double, 16>(s) : launch_r4_t<4, float, 16>(s);

@@ -244,4 +244,225 @@ k_r4(const R4Args<R> a) {
   if (z < ze) { body(R4Phase<8>{}, z); }
 }
 
+
+// accessor for the 9-plane ring of k_r4_async: ring[(PH + i) % 9] = plane z-4+i
+template <typename R, int PH> struct RegNb4A {
+  static constexpr int VX = Vec<R>::N;
+  const R (*ring)[VX];
+  const R *xr;
+  const R (*yc)[VX];
+  int e;
+  template <int DX, int DY, int DZ> __device__ __forceinline__ R at() const {
+    if constexpr (DZ != 0) return ring[(PH + 4 + DZ) % 9][e];
+    else if constexpr (DX != 0) return xr[4 + e + DX];
+    else if constexpr (DY != 0) return yc[4 + DY][e];
+    else return ring[(PH + 4) % 9][e];
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// k_r4_async -- the same schedule with every HBM stream prefetched by cp.async (LDGSTS) instead of through
+// registers.  The ring variant above keeps one plane of (v, u, roc2, halo) in flight per thread: 32 KB
+// per SM, a third short of what 6.5 TB/s x ~1 us of loaded latency needs (Little's law), and deeper
+// register prefetch costs the second CTA per SM.  Here NS = 4 shared-memory stages hold three planes in
+// flight at no register cost:
+//   * group G(p) = { halo strips of plane p -> staged plane buffer p % NS,
+//                    u(p), roc2(p), v(p+4) of my own points -> private 16-byte slots of stage p % NS }
+//     is issued three iterations before plane p is computed, one commit group per plane
+//   * iteration z: cp.async.wait_group(NS-2) (G(z) has landed) -> my centre vector into buffer z % NS ->
+//     __syncthreads -> issue G(z+3) (its buffer was read last in iteration z-1, which every warp has left)
+//     -> compute plane z
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+template <typename R, int NW> struct R4ACfg {
+  using B = R4Cfg<R, NW>;
+  static constexpr int NS = 4;                                  // stages: 3 planes in flight
+  static constexpr int PLANE = B::SROWS * B::SP;                // elements per staged plane
+  static constexpr int NPRIV = 3;                               // private streams: v(p+4), u(p), roc2(p)
+  static constexpr size_t SMEM = ((size_t)NS * PLANE + (size_t)NS * NPRIV * B::NT * B::VX) * sizeof(R);
+};
+
+template <int K, typename R, int NW>
+__global__ void __launch_bounds__(32 * NW)
+k_r4_async(const R4Args<R> a) {
+  using Cfg = R4Cfg<R, NW>;
+  using ACfg = R4ACfg<R, NW>;
+  constexpr int RAD = Cfg::RAD, VX = Cfg::VX, WX = Cfg::WX, H = Cfg::H, NT = Cfg::NT;
+  constexpr int SP = Cfg::SP, HXV = Cfg::HXV, NHV = Cfg::NHV, HPT = Cfg::HPT;
+  constexpr int NS = ACfg::NS, PLANE = ACfg::PLANE, NPRIV = ACfg::NPRIV, RB = 9;
+  constexpr int NCA = KTraits<K>::NCA;
+  constexpr bool TO2 = KTraits<K>::TO == 2;
+  static_assert(KTraits<K>::R == 4, "radius-4 operators only");
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  R *planes = reinterpret_cast<R *>(smem_raw);                 // [NS][SROWS][SP]
+  R *priv = planes + (size_t)NS * PLANE;                        // [NS][NPRIV][NT][VX]
+
+  const DevGrid &g = a.g;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x0t = g.X0 + (int)blockIdx.x * WX, y0t = g.Y0 + (int)blockIdx.y * H;
+  const int x = x0t + lane * VX, y = y0t + warp;
+  const int zb = a.zb0 + (int)blockIdx.z * a.zchunk;
+  const int ze = min(zb + a.zchunk, a.ze0);
+
+  const bool ok = (x + VX <= g.px) && (y < g.ny_dev);
+  unsigned inter = 0;
+#pragma unroll
+  for (int e = 0; e < VX; ++e)
+    if ((x + e < g.X0 + g.nx) && (y < g.Y0 + g.ny)) inter |= 1u << e;
+  const long long off = (long long)y * g.px + x;
+
+  int hs_off[HPT];
+  long long hg_off[HPT];
+  bool h_ok[HPT];
+#pragma unroll
+  for (int h = 0; h < HPT; ++h) {
+    const int item = tid + h * NT;
+    int srow, scol;
+    if (item < 2 * RAD * 32) {
+      const int rr = item >> 5, vv = item & 31;
+      srow = (rr < RAD) ? rr : H + rr;
+      scol = RAD + vv * VX;
+    } else {
+      const int it2 = item - 2 * RAD * 32;
+      const int row = it2 / (2 * HXV), k = it2 % (2 * HXV);
+      const int side = k / HXV, hv = k % HXV;
+      srow = RAD + row;
+      scol = (side == 0) ? hv * VX : RAD + WX + hv * VX;
+    }
+    const int gx = x0t - RAD + scol, gy = y0t - RAD + srow;
+    hs_off[h] = srow * SP + scol;
+    hg_off[h] = (long long)gy * g.px + gx;
+    h_ok[h] = (item < NHV) && (gx >= 0) && (gx + VX <= g.px) && (gy >= 0) && (gy < g.ny_dev);
+  }
+
+  auto priv_slot = [&](int stage, int which) -> R * {
+    return priv + (((size_t)stage * NPRIV + which) * NT + tid) * VX;
+  };
+  // G(p): everything plane p needs from HBM / L2, as one commit group (possibly empty past the chunk)
+  auto issue_group = [&](int p) {
+    if (p < ze && p >= 0 && p < g.nz_dev) {
+      const int st = (p - zb) & (NS - 1);
+      R *buf = planes + (size_t)st * PLANE;
+      const R *pv = a.v + (long long)p * g.pxy;
+#pragma unroll
+      for (int h = 0; h < HPT; ++h)
+        if (h_ok[h]) cp_async16(buf + hs_off[h], pv + hg_off[h]);
+      if (ok) {
+        if (p + 4 < g.nz_dev) cp_async16(priv_slot(st, 0), a.v + off + (long long)(p + 4) * g.pxy);
+        if constexpr (TO2) {
+          cp_async16(priv_slot(st, 1), a.u + off + (long long)p * g.pxy);
+          cp_async16(priv_slot(st, 2), a.roc2 + off + (long long)p * g.pxy);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  R ring[RB][VX];           // ring[(ph + i) % 9] = plane z-4+i (i = 0..7); (ph + 8) % 9 receives plane z+4
+#pragma unroll
+  for (int i = 0; i < RB; ++i)
+#pragma unroll
+    for (int e = 0; e < VX; ++e) ring[i][e] = (R)0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (ok && zb - 4 + i >= 0 && zb - 4 + i < g.nz_dev) ld128<R>(a.v + off + (long long)(zb - 4 + i) * g.pxy, ring[i]);
+  static_assert(NS == 4, "stage index uses a mask");
+  issue_group(zb);
+  issue_group(zb + 1);
+  issue_group(zb + 2);
+
+  auto body = [&](auto phase_tag, const int z) {
+    constexpr int PH = decltype(phase_tag)::value;
+    const int st = (z - zb) & (NS - 1);
+    R *s = planes + (size_t)st * PLANE;
+    cp_async_wait<NS - 2>();                       // G(z) complete (for this thread)
+    // newest plane of my column, u(old) and roc2 of plane z from my private slots
+    ld128s<R>(priv_slot(st, 0), ring[(PH + 8) % RB]);
+    R uo[VX], rc[VX];
+#pragma unroll
+    for (int e = 0; e < VX; ++e) { uo[e] = (R)0; rc[e] = (R)0; }
+    if constexpr (TO2) {
+      ld128s<R>(priv_slot(st, 1), uo);
+      ld128s<R>(priv_slot(st, 2), rc);
+    }
+    st128<R>(s + (RAD + warp) * SP + RAD + lane * VX, ring[(PH + 4) % RB]);
+    __syncthreads();                               // halos of everyone + all centre vectors visible
+    issue_group(z + NS - 1);                       // refills the buffer last read in iteration z-1
+
+    R yc[2 * RAD + 1][VX];
+#pragma unroll
+    for (int q = 0; q < 2 * RAD + 1; ++q)
+      if (q != RAD) ld128s<R>(s + (warp + q) * SP + RAD + lane * VX, yc[q]);
+    R xr[VX + 2 * RAD];
+#pragma unroll
+    for (int q = 0; q < (VX + 2 * RAD) / VX; ++q) {
+      R t[VX];
+      if (q * VX == RAD) {
+#pragma unroll
+        for (int e = 0; e < VX; ++e) t[e] = ring[(PH + 4) % RB][e];
+      } else {
+        ld128s<R>(s + (RAD + warp) * SP + lane * VX + q * VX, t);
+      }
+#pragma unroll
+      for (int e = 0; e < VX; ++e) xr[q * VX + e] = t[e];
+    }
+    R cfr[NCA > 0 ? NCA : 1][VX];
+    if constexpr (NCA > 0) {
+      const R *cp = a.coef + off + (long long)z * g.pxy;
+#pragma unroll
+      for (int m = 0; m < NCA; ++m) {
+#pragma unroll
+        for (int e = 0; e < VX; ++e) cfr[m][e] = (R)0;
+        if (ok) ld128<R>(cp + (long long)m * a.coef_stride, cfr[m]);
+      }
+    }
+    R o[VX];
+#pragma unroll
+    for (int e = 0; e < VX; ++e) {
+      RegNb4A<R, PH> n{ring, xr, yc, e};
+      if constexpr (NCA > 0) {
+        RegCoef<R, NCA> cfp;
+#pragma unroll
+        for (int m = 0; m < NCA; ++m) cfp.v[m] = cfr[m][e];
+        o[e] = StencilExpr<K>::template eval<R>(n, cfp, (R)0, (R)0);
+      } else {
+        o[e] = StencilExpr<K>::template eval<R>(n, a.cc, uo[e], rc[e]);
+      }
+    }
+    R *outp = a.u + off + (long long)z * g.pxy;
+    if (inter == (1u << VX) - 1u) {
+      st128<R>(outp, o);
+    } else if (inter != 0u) {
+#pragma unroll
+      for (int e = 0; e < VX; ++e)
+        if ((inter >> e) & 1u) outp[e] = o[e];
+    }
+  };
+
+  int z = zb;
+  for (; z + RB <= ze; z += RB) {
+    body(R4Phase<0>{}, z);     body(R4Phase<1>{}, z + 1); body(R4Phase<2>{}, z + 2);
+    body(R4Phase<3>{}, z + 3); body(R4Phase<4>{}, z + 4); body(R4Phase<5>{}, z + 5);
+    body(R4Phase<6>{}, z + 6); body(R4Phase<7>{}, z + 7); body(R4Phase<8>{}, z + 8);
+  }
+  if (z < ze) { body(R4Phase<0>{}, z); ++z; }
+  if (z < ze) { body(R4Phase<1>{}, z); ++z; }
+  if (z < ze) { body(R4Phase<2>{}, z); ++z; }
+  if (z < ze) { body(R4Phase<3>{}, z); ++z; }
+  if (z < ze) { body(R4Phase<4>{}, z); ++z; }
+  if (z < ze) { body(R4Phase<5>{}, z); ++z; }
+  if (z < ze) { body(R4Phase<6>{}, z); ++z; }
+  if (z < ze) { body(R4Phase<7>{}, z); }
+  cp_async_wait<0>();
+}
+
 }  // namespace girih

@@ -167,9 +167,12 @@ def test_marching_kernel_tiles(oracle, kernel, dt):
 @pytest.mark.parametrize("kernel", [0, 4])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 def test_radius4_tile_seams(oracle, kernel, dt):
+    # every radius-4 schedule: default (slot 0: cp.async staging, slot 4: strips), ring variants, 16-row CTAs
     for st in ((140, 37, 21), (9, 5, 11), (257, 17, 10)):
-        pb, _, _ = gpu_run(kernel, st, dt, 0, 6, options=(("zchunk", 4),))
-        assert_same(pb, oracle_run(oracle, kernel, st, dt, 0, 6))
+        ob = oracle_run(oracle, kernel, st, dt, 0, 6)
+        for opts in ((("zchunk", 4),), (("tile", 8), ("zchunk", 11)), (("tile", 16),), (("tile", 116), ("zchunk", 5))):
+            pb, _, _ = gpu_run(kernel, st, dt, 0, 6, options=opts)
+            assert_same(pb, ob)
 
 
 @pytest.mark.parametrize("kernel", [0, 1, 2, 3, 4, 5, 7])
