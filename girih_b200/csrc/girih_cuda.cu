@@ -89,6 +89,7 @@ struct girih_gpu_ctx {
   double ms_compute = 0, ms_comm = 0, ms_total = 0;
   int n_kernels = 0, n_passes = 0, n_steps = 0, tfuse_used = 1;
   unsigned long long *d_scan = nullptr;
+  void *d_stage = nullptr;            // linear copy of one host array (fast-path transfers)
   char err[512] = "";
 };
 
@@ -212,6 +213,7 @@ extern "C" void girih_gpu_destroy(girih_gpu_ctx *c) {
   if (c->dU3) cudaFree(c->dU3);
   if (c->dCoef) cudaFree(c->dCoef);
   if (c->d_scan) cudaFree(c->d_scan);
+  if (c->d_stage) cudaFree(c->d_stage);
   for (auto &p : c->comm_ev) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
@@ -303,11 +305,63 @@ extern "C" int girih_gpu_upload(girih_gpu_ctx *c, const void *U1, const void *U2
   return GIRIH_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// fast transfers for page-locked host arrays: ONE linear DMA of the whole host array (full PCIe rate,
+// a pitched 3-D copy moves row by row) plus a device kernel that converts between the reference's
+// host layout and the DevGrid layout.  Used by girih_gpu_upload_fields / girih_gpu_download.
+// ------------------------------------------------------------------------------------------------
+template <typename R, bool TO_DEVICE>
+__global__ void k_repitch(DevGrid g, R *__restrict__ dev, R *__restrict__ lin, int hx, int hy, int hz) {
+  // lin: [hz][hy][hx] (host layout, hx includes the x padding); only the first nx+2r columns are moved
+  const int w = g.nx + 2 * g.r;
+  const long long rows = (long long)hy * hz;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = (int)(row % hy), z = (int)(row / hy);
+    R *d = dev + ((long long)(z + g.Z0 - g.r) * g.ny_dev + (y + g.Y0 - g.r)) * g.px + (g.X0 - g.r);
+    R *l = lin + row * hx;
+    for (int x = threadIdx.x; x < w; x += blockDim.x) {
+      if (TO_DEVICE) d[x] = l[x];
+      else l[x] = d[x];
+    }
+  }
+}
+
+static int ensure_stage(girih_gpu_ctx *c) {
+  if (!c->d_stage) {
+    const size_t bytes = (size_t)c->hshape[0] * c->hshape[1] * c->hshape[2] * c->es;
+    CU(cudaMalloc(&c->d_stage, bytes));
+    // the x padding columns of the host layout are never touched by the steppers; they travel through this
+    // buffer unchanged (zero until an upload brings the host's own padding, which GIRIH's fill leaves zero)
+    CU(cudaMemsetAsync(c->d_stage, 0, bytes, c->s_comp));
+  }
+  return GIRIH_OK;
+}
+
+static int fast_copy(girih_gpu_ctx *c, void *dev, void *host, bool to_device) {
+  int rc = ensure_stage(c);
+  if (rc) return rc;
+  const size_t bytes = (size_t)c->hshape[0] * c->hshape[1] * c->hshape[2] * c->es;
+  const int grid = 148 * 16;
+  if (to_device) {
+    CU(cudaMemcpyAsync(c->d_stage, host, bytes, cudaMemcpyHostToDevice, c->s_comp));
+    if (c->es == 8) k_repitch<double, true><<<grid, 256, 0, c->s_comp>>>(c->g, (double *)dev, (double *)c->d_stage, c->hshape[0], c->hshape[1], c->hshape[2]);
+    else            k_repitch<float, true><<<grid, 256, 0, c->s_comp>>>(c->g, (float *)dev, (float *)c->d_stage, c->hshape[0], c->hshape[1], c->hshape[2]);
+    CU(cudaGetLastError());
+  } else {
+    if (c->es == 8) k_repitch<double, false><<<grid, 256, 0, c->s_comp>>>(c->g, (double *)dev, (double *)c->d_stage, c->hshape[0], c->hshape[1], c->hshape[2]);
+    else            k_repitch<float, false><<<grid, 256, 0, c->s_comp>>>(c->g, (float *)dev, (float *)c->d_stage, c->hshape[0], c->hshape[1], c->hshape[2]);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->s_comp));
+  }
+  return GIRIH_OK;
+}
+
 extern "C" int girih_gpu_upload_fields(girih_gpu_ctx *c, const void *U1, const void *U2) {
   if (!c || !c->uploaded) return fail(c, GIRIH_ERR_STATE, "upload_fields before upload");
   CU(cudaSetDevice(c->device));
-  if (U1) CU(copy3d(c, c->dU[0], U1, true, c->s_comp, true));
-  if (U2) CU(copy3d(c, c->dU[1], U2, true, c->s_comp, true));
+  int rc;
+  if (U1 && (rc = fast_copy(c, c->dU[0], const_cast<void *>(U1), true))) return rc;
+  if (U2 && (rc = fast_copy(c, c->dU[1], const_cast<void *>(U2), true))) return rc;
   CU(cudaStreamSynchronize(c->s_comp));
   return GIRIH_OK;
 }
@@ -316,8 +370,9 @@ extern "C" int girih_gpu_download(girih_gpu_ctx *c, void *U1, void *U2) {
   if (!c) return GIRIH_ERR_ARG;
   if (!c->uploaded) return fail(c, GIRIH_ERR_STATE, "download before upload");
   CU(cudaSetDevice(c->device));
-  if (U1) CU(copy3d(c, c->dU[0], U1, false, c->s_comp, true));
-  if (U2) CU(copy3d(c, c->dU[1], U2, false, c->s_comp, true));
+  int rc;
+  if (U1 && (rc = fast_copy(c, c->dU[0], U1, false))) return rc;
+  if (U2 && (rc = fast_copy(c, c->dU[1], U2, false))) return rc;
   CU(cudaStreamSynchronize(c->s_comp));
   return GIRIH_OK;
 }
