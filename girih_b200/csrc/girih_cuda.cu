@@ -84,7 +84,7 @@ struct girih_gpu_ctx {
   // NCCL
   ncclComm_t comm = nullptr;
   // options
-  int opt_variant = 0, opt_zchunk = 0, opt_tile = 0, opt_overlap = 0;
+  int opt_variant = 0, opt_zchunk = 0, opt_tile = 0, opt_overlap = 0, opt_contract = 0;
   // accounting of the last run
   double ms_compute = 0, ms_comm = 0, ms_total = 0;
   int n_kernels = 0, n_passes = 0, n_steps = 0, tfuse_used = 1;
@@ -230,6 +230,7 @@ extern "C" int girih_gpu_set_option(girih_gpu_ctx *c, const char *key, int value
   else if (!strcmp(key, "zchunk")) c->opt_zchunk = value;
   else if (!strcmp(key, "tile")) c->opt_tile = value;
   else if (!strcmp(key, "overlap")) c->opt_overlap = value;
+  else if (!strcmp(key, "contract")) c->opt_contract = (value != 0);
   else return fail(c, GIRIH_ERR_ARG, "unknown option '%s'", key);
   return GIRIH_OK;
 }
@@ -475,14 +476,14 @@ template <typename R> static ConstCoef<R> make_cc(const girih_gpu_ctx *c) {
 }
 
 // ---- naive: one step over a device-coordinate box -------------------------------------------
-template <int K, typename R>
+template <int K, typename R, bool FM>
 static cudaError_t launch_naive_t(girih_gpu_ctx *c, int dst, int xb, int yb, int zb, int xe, int ye, int ze) {
   if (xe <= xb || ye <= yb || ze <= zb) return cudaSuccess;
   dim3 block(64, 4, 1);
   dim3 grid((xe - xb + 63) / 64, (ye - yb + 3) / 4, ze - zb);
   R *u = (R *)c->dU[dst];
   const R *v = (const R *)c->dU[dst ^ 1];
-  k_naive<K, R><<<grid, block, 0, c->s_comp>>>(c->g, u, v, (const R *)c->dU3, (const R *)c->dCoef,
+  k_naive<K, R, FM><<<grid, block, 0, c->s_comp>>>(c->g, u, v, (const R *)c->dU3, (const R *)c->dCoef,
                                               (long long)c->arr_elems, make_cc<R>(c), xb, yb, zb, xe, ye, ze);
   c->n_kernels++;
   return cudaGetLastError();
@@ -490,8 +491,11 @@ static cudaError_t launch_naive_t(girih_gpu_ctx *c, int dst, int xb, int yb, int
 static cudaError_t launch_naive(girih_gpu_ctx *c, int dst, int xb, int yb, int zb, int xe, int ye, int ze) {
 #define GN(K)                                                                          \
   case K:                                                                              \
-    return c->es == 8 ? launch_naive_t<K, double>(c, dst, xb, yb, zb, xe, ye, ze)      \
-                      : launch_naive_t<K, float>(c, dst, xb, yb, zb, xe, ye, ze);
+    if (c->opt_contract)                                                               \
+      return c->es == 8 ? launch_naive_t<K, double, true>(c, dst, xb, yb, zb, xe, ye, ze)  \
+                        : launch_naive_t<K, float, true>(c, dst, xb, yb, zb, xe, ye, ze);  \
+    return c->es == 8 ? launch_naive_t<K, double, false>(c, dst, xb, yb, zb, xe, ye, ze)   \
+                      : launch_naive_t<K, float, false>(c, dst, xb, yb, zb, xe, ye, ze);
   switch (c->kernel) { GN(0) GN(1) GN(2) GN(3) GN(4) GN(5) GN(7) default: return cudaErrorInvalidValue; }
 #undef GN
 }
@@ -523,6 +527,7 @@ static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb
   sl.zchunk = c->opt_zchunk;
   sl.tile = c->opt_tile;
   sl.variant = c->opt_variant;
+  sl.contract = c->opt_contract;
   sl.stream = c->s_comp;
   c->n_kernels++;
   if (g.r == 1) return launch_r1(c->kernel, c->es, T, sl);

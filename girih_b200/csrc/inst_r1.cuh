@@ -62,10 +62,16 @@ static cudaError_t launch_r1_t(const StreamLaunch &s) {
 // tile shapes instantiated per (operator, precision, depth); "tile" option = PY*100 + NW
 template <int K, typename R, int T>
 static cudaError_t launch_r1_tile(const StreamLaunch &s) {
+  if (s.contract) {   // contracted arithmetic: the default tile of each (operator, precision) only
+    if constexpr (KTraits<K>::NCA == 0 && sizeof(R) == 8) return launch_r1_t<K, R, T, 4, 8, R1_FM>(s);
+    else return launch_r1_t<K, R, T, 2, 16, R1_FM>(s);
+  }
   if (s.tile == 216) return launch_r1_t<K, R, T, 2, 16>(s);
   if (s.tile == 408) return launch_r1_t<K, R, T, 4, 8>(s);
   if constexpr (K == 1 && sizeof(R) == 8 && T == 4) {   // perf experiments only (results invalid)
     if (s.tile == 1408) return launch_r1_t<K, R, T, 4, 8, 1>(s);
+    if (s.tile == 8408) return launch_r1_t<K, R, T, 4, 8, 8>(s);
+    if (s.tile == 16408) return launch_r1_t<K, R, T, 4, 8, 16>(s);
     if (s.tile == 2408) return launch_r1_t<K, R, T, 4, 8, 2>(s);
     if (s.tile == 3408) return launch_r1_t<K, R, T, 4, 8, 3>(s);
     if (s.tile == 3216) return launch_r1_t<K, R, T, 2, 16, 3>(s);
@@ -85,7 +91,7 @@ static cudaError_t launch_r1_tile(const StreamLaunch &s) {
 }
 
 // single-step pass: the barrier-free marching kernel
-template <int K, typename R, int PY, int NWY>
+template <int K, typename R, int PY, int NWY, bool FM = false>
 static cudaError_t launch_march_t(const StreamLaunch &s) {
   const DevGrid &g = s.g;
   constexpr int WX = 32 * Vec<R>::N;
@@ -110,13 +116,17 @@ static cudaError_t launch_march_t(const StreamLaunch &s) {
   zchunk = std::min(zchunk, std::max(nz, 1));
   a.zchunk = zchunk;
   dim3 grid((g.nx + WX - 1) / WX, (g.ny + TY - 1) / TY, (nz + zchunk - 1) / zchunk);
-  k_r1_march<K, R, PY, NWY><<<grid, 32 * NWY, 0, s.stream>>>(a);
+  k_r1_march<K, R, PY, NWY, FM><<<grid, 32 * NWY, 0, s.stream>>>(a);
   return cudaGetLastError();
 }
 
 template <int K, typename R>
 static cudaError_t launch_r1_depth(int T, const StreamLaunch &s) {
   if (T == 1 && s.variant != 2) {
+    if (s.contract) {
+      if constexpr (K == 1 || K == 5) return launch_march_t<K, R, 4, 4, true>(s);
+      else return launch_march_t<K, R, 2, 8, true>(s);
+    }
     // tile option for the marching kernel: PY*100 + NWY
     if (s.tile == 108) return launch_march_t<K, R, 1, 8>(s);
     if (s.tile == 208) return launch_march_t<K, R, 2, 8>(s);

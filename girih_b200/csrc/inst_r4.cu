@@ -33,7 +33,7 @@ static cudaError_t launch_r4_t(const StreamLaunch &s) {
   return cudaGetLastError();
 }
 
-template <int K, typename R, int PY, int NW>
+template <int K, typename R, int PY, int NW, bool FM = false>
 static cudaError_t launch_r4_strip_t(const StreamLaunch &s) {
   using Cfg = R4StripCfg<R, PY, NW>;
   const DevGrid &g = s.g;
@@ -57,14 +57,14 @@ static cudaError_t launch_r4_strip_t(const StreamLaunch &s) {
   }
   a.zchunk = zchunk;
   dim3 grid(ntx, nty, (s.ze0 - s.zb0 + zchunk - 1) / zchunk);
-  auto kfn = k_r4_strip<K, R, PY, NW>;
+  auto kfn = k_r4_strip<K, R, PY, NW, FM>;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
   if (e != cudaSuccess) return e;
   kfn<<<grid, 32 * NW, Cfg::SMEM, s.stream>>>(a);
   return cudaGetLastError();
 }
 
-template <int K, typename R, int NW>
+template <int K, typename R, int NW, bool FM = false>
 static cudaError_t launch_r4_async_t(const StreamLaunch &s) {
   using Cfg = R4Cfg<R, NW>;
   using ACfg = R4ACfg<R, NW>;
@@ -84,7 +84,7 @@ static cudaError_t launch_r4_async_t(const StreamLaunch &s) {
   if (zchunk <= 0) zchunk = std::max(1, std::min(s.ze0 - s.zb0, 64));
   a.zchunk = zchunk;
   dim3 grid(ntx, nty, (s.ze0 - s.zb0 + zchunk - 1) / zchunk);
-  auto kfn = k_r4_async<K, R, NW>;
+  auto kfn = k_r4_async<K, R, NW, FM>;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACfg::SMEM);
   if (e != cudaSuccess) return e;
   kfn<<<grid, 32 * NW, ACfg::SMEM, s.stream>>>(a);
@@ -95,6 +95,11 @@ cudaError_t launch_r4(int kernel, int es, const StreamLaunch &s) {
   // tile option = warps (rows) per CTA
   // tile option: 8 / 16 = ring variant with that many rows per CTA, 116 = cp.async variant with 16 rows;
   // default = cp.async variant, 8 rows per CTA (measured fastest: 88-90% of the HBM peak at 512^3)
+  if (s.contract) {   // contracted arithmetic: default kernels only
+    if (kernel == 0) return es == 8 ? launch_r4_async_t<0, double, 8, true>(s) : launch_r4_async_t<0, float, 8, true>(s);
+    if (kernel == 4) return es == 8 ? launch_r4_strip_t<4, double, 2, 8, true>(s) : launch_r4_strip_t<4, float, 2, 8, true>(s);
+    return cudaErrorInvalidValue;
+  }
   if (kernel == 0) {
     if (s.tile == 8) return es == 8 ? launch_r4_t<0, double, 8>(s) : launch_r4_t<0, float, 8>(s);
     if (s.tile == 16) return es == 8 ? launch_r4_t<0, double, 16>(s) : launch_r4_t<0, float, 16>(s);

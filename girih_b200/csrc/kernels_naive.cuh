@@ -9,7 +9,7 @@
 
 namespace girih {
 
-template <int K, typename R>
+template <int K, typename R, bool FM = false>
 __global__ void __launch_bounds__(256)
 k_naive(DevGrid g, R *__restrict__ u, const R *__restrict__ v, const R *__restrict__ roc2,
         const R *__restrict__ coef, long long coef_stride, ConstCoef<R> cc,
@@ -25,9 +25,9 @@ k_naive(DevGrid g, R *__restrict__ u, const R *__restrict__ v, const R *__restri
   R out;
   if constexpr (KTraits<K>::NCA > 0) {
     PointCoef<R> cf{coef + idx, coef_stride};
-    out = StencilExpr<K>::template eval<R>(n, cf, uold, rc);
+    out = StencilExpr<K>::template eval<R, FM>(n, cf, uold, rc);
   } else {
-    out = StencilExpr<K>::template eval<R>(n, cc, uold, rc);
+    out = StencilExpr<K>::template eval<R, FM>(n, cc, uold, rc);
   }
   u[idx] = out;
 }

@@ -65,6 +65,8 @@ template <typename R> struct RegNb1 {
   }
 };
 
+constexpr int R1_FM = 32;   // DBG flag bit: evaluate with the reference's gcc -mfma contraction
+
 template <int PH> struct Phase { static constexpr int value = PH; };
 template <int I> struct Level { static constexpr int value = I; };
 template <bool B> struct FrameTag { static constexpr bool value = B; };
@@ -82,6 +84,7 @@ k_r1(const R1Args<R> a) {
   constexpr int VX = Cfg::VX, WX = Cfg::WX, HX = Cfg::HX, UX = Cfg::UX, H = Cfg::H, UY = Cfg::UY;
   constexpr int PF = Cfg::PF;
   constexpr int NCA = KTraits<K>::NCA;
+  constexpr bool FM = (DBG & R1_FM) != 0;   // contracted (FMA) arithmetic, see stencil_expr.cuh
   constexpr unsigned ALL = (PY * VX >= 32) ? 0xffffffffu : ((1u << (PY * VX)) - 1u);
   static_assert(KTraits<K>::R == 1 && KTraits<K>::TO == 1, "radius-1, first-order-in-time only");
   static_assert(PY * VX <= 32, "point masks are 32 bits");
@@ -255,9 +258,9 @@ k_r1(const R1Args<R> a) {
             RegCoef<R, NCA> rc;
 #pragma unroll
             for (int m = 0; m < NCA; ++m) rc.v[m] = cf[m][e];
-            O[j][e] = StencilExpr<K>::template eval<R>(n, rc, (R)0, (R)0);
+            O[j][e] = StencilExpr<K>::template eval<R, FM>(n, rc, (R)0, (R)0);
           } else {
-            O[j][e] = StencilExpr<K>::template eval<R>(n, a.cc, (R)0, (R)0);
+            O[j][e] = StencilExpr<K>::template eval<R, FM>(n, a.cc, (R)0, (R)0);
           }
         }
       }
@@ -304,7 +307,9 @@ k_r1(const R1Args<R> a) {
   // planes zin-T .. zin-1 are produced in iteration `it`; the version is chosen per iteration
   auto step = [&](auto phase_tag, const int it) {
     const int zin = zb - T + it;
-    if (warp_masked || (zin - T < g.zlo) || (zin > g.zhi)) body(phase_tag, FrameTag<true>{}, it);
+    if constexpr (DBG & 8) body(phase_tag, FrameTag<false>{}, it);       // experiment (results invalid)
+    else if constexpr (DBG & 16) body(phase_tag, FrameTag<true>{}, it);   // experiment
+    else if (warp_masked || (zin - T < g.zlo) || (zin > g.zhi)) body(phase_tag, FrameTag<true>{}, it);
     else body(phase_tag, FrameTag<false>{}, it);
   };
   int it = 0;

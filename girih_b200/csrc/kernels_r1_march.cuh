@@ -48,7 +48,7 @@ template <int I> struct MPhase { static constexpr int value = I; };
 template <bool B> struct MFull { static constexpr bool value = B; };
 
 // NWY warps per CTA, PY rows per thread: CTA tile = (32*VX) x (NWY*PY)
-template <int K, typename R, int PY, int NWY>
+template <int K, typename R, int PY, int NWY, bool FM = false>
 __global__ void __launch_bounds__(32 * NWY)
 k_r1_march(const MarchArgs<R> a) {
   constexpr int VX = Vec<R>::N, WX = 32 * VX, RB = 4;
@@ -163,9 +163,9 @@ k_r1_march(const MarchArgs<R> a) {
             RegCoef<R, NCA> rc;
 #pragma unroll
             for (int m = 0; m < NCA; ++m) rc.v[m] = cf[m][e];
-            o[e] = StencilExpr<K>::template eval<R>(n, rc, (R)0, (R)0);
+            o[e] = StencilExpr<K>::template eval<R, FM>(n, rc, (R)0, (R)0);
           } else {
-            o[e] = StencilExpr<K>::template eval<R>(n, a.cc, (R)0, (R)0);
+            o[e] = StencilExpr<K>::template eval<R, FM>(n, a.cc, (R)0, (R)0);
           }
         }
         if constexpr (FULL) {

@@ -66,7 +66,7 @@ template <typename R, int PH> struct RegNb4 {
 
 template <int I> struct R4Phase { static constexpr int value = I; };
 
-template <int K, typename R, int NW>
+template <int K, typename R, int NW, bool FM = false>
 __global__ void __launch_bounds__(32 * NW)
 k_r4(const R4Args<R> a) {
   using Cfg = R4Cfg<R, NW>;
@@ -211,9 +211,9 @@ k_r4(const R4Args<R> a) {
         RegCoef<R, NCA> cfp;
 #pragma unroll
         for (int m = 0; m < NCA; ++m) cfp.v[m] = cfr[m][e];
-        o[e] = StencilExpr<K>::template eval<R>(n, cfp, (R)0, (R)0);
+        o[e] = StencilExpr<K>::template eval<R, FM>(n, cfp, (R)0, (R)0);
       } else {
-        o[e] = StencilExpr<K>::template eval<R>(n, a.cc, uo[PAR][e], rc[PAR][e]);
+        o[e] = StencilExpr<K>::template eval<R, FM>(n, a.cc, uo[PAR][e], rc[PAR][e]);
       }
     }
     R *outp = a.u + off + (long long)z * g.pxy;
@@ -290,7 +290,7 @@ template <typename R, int NW> struct R4ACfg {
   static constexpr size_t SMEM = ((size_t)NS * PLANE + (size_t)NS * NPRIV * B::NT * B::VX) * sizeof(R);
 };
 
-template <int K, typename R, int NW>
+template <int K, typename R, int NW, bool FM = false>
 __global__ void __launch_bounds__(32 * NW)
 k_r4_async(const R4Args<R> a) {
   using Cfg = R4Cfg<R, NW>;
@@ -433,9 +433,9 @@ k_r4_async(const R4Args<R> a) {
         RegCoef<R, NCA> cfp;
 #pragma unroll
         for (int m = 0; m < NCA; ++m) cfp.v[m] = cfr[m][e];
-        o[e] = StencilExpr<K>::template eval<R>(n, cfp, (R)0, (R)0);
+        o[e] = StencilExpr<K>::template eval<R, FM>(n, cfp, (R)0, (R)0);
       } else {
-        o[e] = StencilExpr<K>::template eval<R>(n, a.cc, uo[e], rc[e]);
+        o[e] = StencilExpr<K>::template eval<R, FM>(n, a.cc, uo[e], rc[e]);
       }
     }
     R *outp = a.u + off + (long long)z * g.pxy;

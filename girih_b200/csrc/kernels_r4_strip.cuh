@@ -54,7 +54,7 @@ template <typename R, int PY> struct RegNb4Strip {
   }
 };
 
-template <int K, typename R, int PY, int NW>
+template <int K, typename R, int PY, int NW, bool FM = false>
 __global__ void __launch_bounds__(32 * NW)
 k_r4_strip(const R4Args<R> a) {
   using Cfg = R4StripCfg<R, PY, NW>;
@@ -245,9 +245,9 @@ k_r4_strip(const R4Args<R> a) {
           RegCoef<R, NCA> cfp;
 #pragma unroll
           for (int m = 0; m < NCA; ++m) cfp.v[m] = cfr[m][e];
-          o[e] = StencilExpr<K>::template eval<R>(n, cfp, (R)0, (R)0);
+          o[e] = StencilExpr<K>::template eval<R, FM>(n, cfp, (R)0, (R)0);
         } else {
-          o[e] = StencilExpr<K>::template eval<R>(n, a.cc, uo[j][e], rc[j][e]);
+          o[e] = StencilExpr<K>::template eval<R, FM>(n, a.cc, uo[j][e], rc[j][e]);
         }
       }
       const unsigned m = (interior_xy >> (j * VX)) & ((1u << VX) - 1u);

@@ -19,6 +19,7 @@ struct StreamLaunch {
   int zchunk;            // 0 = choose
   int tile;              // 0 = default, else PY*100 + NW
   int variant;           // 0 = auto, 2 = force the fused-sweep kernel also for T = 1
+  int contract;          // 1 = FMA-contracted arithmetic (stencil_expr.cuh, Sop<R, true>); default tiles only
   cudaStream_t stream;
 };
 

@@ -312,6 +312,7 @@ void gpu_attach(Parameters *p) {
   }
   gpu_check(p, girih_gpu_set_option(p->gpu, "variant", p->gpu_variant), "girih_gpu_set_option");
   gpu_check(p, girih_gpu_set_option(p->gpu, "overlap", p->gpu_overlap), "girih_gpu_set_option");
+  gpu_check(p, girih_gpu_set_option(p->gpu, "contract", p->gpu_contract), "girih_gpu_set_option");
   gpu_check(p, girih_gpu_upload(p->gpu, p->U1, p->U2, p->U3, p->coef), "girih_gpu_upload");
 }
 

@@ -179,7 +179,13 @@ int girih_gpu_scan_u1(girih_gpu_ctx *ctx, uint64_t *n_nan_inf, uint64_t *n_zero)
  *   "zchunk"   output planes per CTA (0 = choose)
  *   "tile"     fused sweep: PY*100 + NW (rows per thread, warps per CTA); marching kernel: rows per CTA
  *   "overlap"  fused passes: compute the slab boundaries first and overlap the deep-halo exchange with
- *              the interior (default 0: one exchange per pass, ordered before it, measured faster) */
+ *              the interior (default 0: one exchange per pass, ordered before it, measured faster)
+ *   "contract" arithmetic of the per-point expression.  0 (default): every product and sum rounded
+ *              separately -- bit-identical to the reference built without FMA (conf/make.conf.gcc, `-O3`)
+ *              and to its -O0 verifier (src/verification.c).  1: the fused multiply-adds gcc emits for the
+ *              same FUNC_BODY under `-O3 -mfma` (first product fused onto the second, later products
+ *              onto the running sum) -- bit-identical to the reference built that way; 30 % fewer FP64
+ *              instructions per lattice update.  With 1 the "tile" option is ignored (default tiles). */
 int girih_gpu_set_option(girih_gpu_ctx *ctx, const char *key, int value);
 
 const char *girih_gpu_strerror(int status);

@@ -31,12 +31,27 @@
 #define ORACLE_DP 1
 #endif
 
+/* ORACLE_FMA=1: the same source compiled with -mfma -ffp-contract=fast (suffix _dpf/_spf): gcc then
+ * contracts the expressions below exactly as it contracts the reference's FUNC_BODY in the *_fast
+ * reference builds (oracle/Makefile RFAST) -- the checker for the library's "contract" option. */
+#ifndef ORACLE_FMA
+#define ORACLE_FMA 0
+#endif
+
 #if ORACLE_DP
 typedef double real_t;                 /* src/data_structures.h:99-101 */
+#if ORACLE_FMA
+#define SFX(name) name##_dpf
+#else
 #define SFX(name) name##_dp
+#endif
 #else
 typedef float real_t;                  /* src/data_structures.h:102-105 */
+#if ORACLE_FMA
+#define SFX(name) name##_spf
+#else
 #define SFX(name) name##_sp
+#endif
 #endif
 
 /* operator registry, src/kernels/stencils.c:260-271 */
@@ -57,7 +72,7 @@ static const kinfo_t KINFO[8] = {
 static const double G_COEF[11] = {-0.28472, 0.16000, -0.02000, 0.00254,
     -0.00018, -0.18472, 0.19, -0.0500, 0.00554, -0.0009, 0.00354};
 
-#if ORACLE_DP
+#if ORACLE_DP && !ORACLE_FMA
 /* kernel_info(k, out[5]) -> r, time_order, nd, coeff kind, is_box; returns 0 if k valid */
 int oracle_kernel_info(int k, int out[5])
 {

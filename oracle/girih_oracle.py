@@ -129,21 +129,26 @@ def make_problem(kernel, stencil, dtype=np.float64, alignment=8, padding=True,
     return Problem(kernel, dtype, tuple(stencil), shape, info.r, U1, U2, U3, coef)
 
 
-def step(kernel, shape, box, coef, u, v, roc2):
+def _fsfx(dtype, contract) -> str:
+    """contract=True selects the copy of the oracle compiled with gcc's FMA contraction (_dpf/_spf)."""
+    return _sfx(dtype) + ("f" if contract else "")
+
+
+def step(kernel, shape, box, coef, u, v, roc2, contract=False):
     """u <- one stencil application of v over box=(xb,yb,zb,xe,ye,ze)."""
-    getattr(lib(), "oracle_step_" + _sfx(u.dtype))(
+    getattr(lib(), "oracle_step_" + _fsfx(u.dtype, contract))(
         kernel, _i3(shape), *[int(b) for b in box], _p(coef), _p(u), _p(v), _p(roc2))
 
 
-def run_naive(pb: Problem, nt: int) -> None:
+def run_naive(pb: Problem, nt: int, contract=False) -> None:
     """The reference's ts 0 loop (nb_naive_ts.c:187-203): nt rounded up to even steps."""
-    getattr(lib(), "oracle_run_naive_" + _sfx(pb.dtype))(
+    getattr(lib(), "oracle_run_naive_" + _fsfx(pb.dtype, contract))(
         pb.kernel, _i3(pb.shape), pb.stencil[0], nt, _p(pb.coef), _p(pb.U1), _p(pb.U2), _p(pb.U3))
 
 
-def run_steps(pb: Problem, nsteps: int) -> None:
+def run_steps(pb: Problem, nsteps: int, contract=False) -> None:
     """Exactly nsteps steps, odd steps writing U1 (what ts 2 leaves: nsteps = nt-1)."""
-    getattr(lib(), "oracle_run_steps_" + _sfx(pb.dtype))(
+    getattr(lib(), "oracle_run_steps_" + _fsfx(pb.dtype, contract))(
         pb.kernel, _i3(pb.shape), pb.stencil[0], nsteps, _p(pb.coef), _p(pb.U1), _p(pb.U2), _p(pb.U3))
 
 
@@ -160,9 +165,10 @@ def compare(ref_full, target_interior, stencil, r):
 # ----------------------------------------------------------------------------------------------
 # the real reference (oracle/_ref), when present
 # ----------------------------------------------------------------------------------------------
-def ref_dump(kernel, stencil, nt, dtype=np.float64, ts=0, extra=(), threads=2):
-    """Run the unmodified reference stepper and return (U1 full domain [z,y,x], r, nt_effective)."""
-    exe = os.path.join(REF_DIR, "ref_dump_" + _sfx(dtype))
+def ref_dump(kernel, stencil, nt, dtype=np.float64, ts=0, extra=(), threads=2, fast=False):
+    """Run the unmodified reference stepper and return (U1 full domain [z,y,x], r, nt_effective).
+    fast=True uses the build with FMA contraction (-O3 -mfma -ffp-contract=fast)."""
+    exe = os.path.join(REF_DIR, "ref_dump_" + _sfx(dtype) + ("_fast" if fast else ""))
     with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
         path = f.name
     try:

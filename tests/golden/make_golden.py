@@ -12,6 +12,10 @@ interior of p.U1 is stored:
   * larger cases -> tests/golden/checksums.json (sha256 over the interior bytes, [z][y][x] order)
 The reference ships no golden vectors of its own; these are outputs of the
 reference itself, which is what its --verify mode compares against bit for bit.
+
+`python tests/golden/make_golden.py fma` writes small_fma.npz / checksums_fma.json instead: the same
+cases run by the reference built with FMA contraction (oracle/_ref/ref_dump_*_fast, gcc -O3 -mfma
+-ffp-contract=fast) -- the fixtures for the library's "contract" option.
 """
 import hashlib
 import json
@@ -50,29 +54,30 @@ def key(k, st, nt, ts, t_dim, dt):
     return f"k{k}_{st[0]}x{st[1]}x{st[2]}_nt{nt}_ts{ts}_td{t_dim}_{dt}"
 
 
-def main():
+def main(fast=False):
     assert O.have_ref(), "build the reference first: make -C oracle ref"
     small, sums = {}, {}
+    tag = "_fma" if fast else ""
     for dt, name in ((np.float32, "sp"), (np.float64, "dp")):
         for (k, st, nt, ts, td) in SMALL:
-            U1, r, nte = O.ref_dump(k, st, nt, dt, ts, ts_extra(ts, td), threads=1 if ts == 2 else 2)
+            U1, r, nte = O.ref_dump(k, st, nt, dt, ts, ts_extra(ts, td), threads=1 if ts == 2 else 2, fast=fast)
             nx, ny, nz = st
             small[key(k, st, nt, ts, td, name)] = U1[r:r + nz, r:r + ny, r:r + nx].copy()
             small[key(k, st, nt, ts, td, name) + "_nteff"] = np.int32(nte)
         for (k, st, nt, ts, td) in LARGE:
             if dt == np.float32 and k == 0 and nt > 60:
                 continue
-            U1, r, nte = O.ref_dump(k, st, nt, dt, ts, ts_extra(ts, td), threads=4 if ts == 2 else 8)
+            U1, r, nte = O.ref_dump(k, st, nt, dt, ts, ts_extra(ts, td), threads=4 if ts == 2 else 8, fast=fast)
             nx, ny, nz = st
             it = np.ascontiguousarray(U1[r:r + nz, r:r + ny, r:r + nx])
             sums[key(k, st, nt, ts, td, name)] = {
                 "sha256": hashlib.sha256(it.tobytes()).hexdigest(), "nt_effective": nte,
                 "max_abs": float(np.abs(it).max())}
-    np.savez_compressed(os.path.join(HERE, "small.npz"), **small)
-    with open(os.path.join(HERE, "checksums.json"), "w") as f:
+    np.savez_compressed(os.path.join(HERE, "small%s.npz" % tag), **small)
+    with open(os.path.join(HERE, "checksums%s.json" % tag), "w") as f:
         json.dump(sums, f, indent=1, sort_keys=True)
     print(len(small) // 2, "small cases,", len(sums), "checksums")
 
 
 if __name__ == "__main__":
-    main()
+    main(fast=(len(sys.argv) > 1 and sys.argv[1] == "fma"))

@@ -18,6 +18,8 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 SMALL = np.load(os.path.join(HERE, "golden", "small.npz"))
 SUMS = json.load(open(os.path.join(HERE, "golden", "checksums.json")))
+SMALL_FMA = np.load(os.path.join(HERE, "golden", "small_fma.npz"))       # reference built with -mfma
+SUMS_FMA = json.load(open(os.path.join(HERE, "golden", "checksums_fma.json")))
 KEY = re.compile(r"k(\d)_(\d+)x(\d+)x(\d+)_nt(\d+)_ts(\d)_td(\d)_(sp|dp)$")
 TOL = {np.dtype(np.float64): 1e-12, np.dtype(np.float32): 1e-5}   # north star, relative L-inf
 
@@ -40,13 +42,13 @@ def gpu_run(kernel, st, dt, ts, nt, t_dim=1, tfuse=0, options=()):
     return pb, nt_eff, info
 
 
-def oracle_run(O, kernel, st, dt, ts, nt, t_dim=1):
+def oracle_run(O, kernel, st, dt, ts, nt, t_dim=1, contract=False):
     ob = O.make_problem(kernel, st, dt)
     if ts == 2:
         nt = O.diamond_round_nt(nt, t_dim)
-        O.run_steps(ob, nt - 1)
+        O.run_steps(ob, nt - 1, contract=contract)
     else:
-        O.run_naive(ob, nt)
+        O.run_naive(ob, nt, contract=contract)
     return ob
 
 
@@ -78,6 +80,64 @@ def test_golden_checksums(key):
     assert nte == SUMS[key]["nt_effective"]
     got = np.ascontiguousarray(pb.interior())
     assert hashlib.sha256(got.tobytes()).hexdigest() == SUMS[key]["sha256"]
+
+
+# ---- "contract" option: the arithmetic of the reference built with FMA contraction ---------------
+CONTRACT = (("contract", 1),)
+
+
+@pytest.mark.parametrize("key", sorted(k for k in SMALL_FMA.files if not k.endswith("_nteff")))
+def test_contracted_golden_small(key):
+    """contract=1 vs outputs of the reference compiled with gcc -O3 -mfma (small_fma.npz): bit-exact."""
+    k, st, nt, ts, td, dt = parse(key)
+    pb, _, _ = gpu_run(k, st, dt, ts, nt, td, options=CONTRACT)
+    assert pb.interior().tobytes() == SMALL_FMA[key].tobytes()
+
+
+@pytest.mark.parametrize("key", sorted(SUMS_FMA))
+def test_contracted_golden_checksums(key):
+    k, st, nt, ts, td, dt = parse(key)
+    pb, nte, _ = gpu_run(k, st, dt, ts, nt, td, options=CONTRACT)
+    assert nte == SUMS_FMA[key]["nt_effective"]
+    got = np.ascontiguousarray(pb.interior())
+    assert hashlib.sha256(got.tobytes()).hexdigest() == SUMS_FMA[key]["sha256"]
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 3, 4, 5, 7])
+def test_contracted_matrix(oracle, kernel, dt):
+    """every operator, single-step and fused schedules, naive and streamed kernels, against the oracle
+    compiled with the same contraction; also within the north-star tolerance of the strict result"""
+    r = G.kernel_info(kernel).r
+    for st in ((150, 71, 23), (32, 64, 16)):
+        for ts, opts in ((0, ()), (2, ()), (0, (("variant", 1),))):
+            nt = max(10, st[0] // r // 2)
+            t_dim = 1
+            if ts == 2:
+                st2 = (st[0], (t_dim + 1) * 2 * r * 4, st[2])
+            else:
+                st2 = st
+            pb, _, _ = gpu_run(kernel, st2, dt, ts, nt, t_dim, options=CONTRACT + opts)
+            assert_same(pb, oracle_run(oracle, kernel, st2, dt, ts, nt, t_dim, contract=True))
+    strict = oracle_run(oracle, kernel, st2, dt, 0, nt)
+    rel = np.abs(pb.U1.astype(np.float64) - strict.U1.astype(np.float64)).max() / np.abs(strict.U1).max()
+    assert 0 < rel <= TOL[np.dtype(dt)]
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("kernel,tfuse", [(1, 1), (1, 2), (1, 3), (1, 4), (2, 3), (3, 2), (5, 1)])
+def test_contracted_fused_depths(oracle, kernel, tfuse, dt):
+    for st, nsteps in (((150, 71, 23), 9), ((61, 34, 9), 12)):
+        pb = G.make_problem(kernel, st, dt)
+        s = G.GpuStepper.for_problem(pb)
+        s.set_option("contract", 1)
+        s.set_option("variant", 2)
+        s.run_fused(nsteps, tfuse)
+        s.download(pb.U1, pb.U2)
+        s.close()
+        ob = oracle.make_problem(kernel, st, dt)
+        oracle.run_steps(ob, nsteps, contract=True)
+        assert_same(pb, ob)
 
 
 # the reference's regression matrix, scripts/verification/verification_std.py:8-34 (single rank):
@@ -288,6 +348,19 @@ def test_cli_verify(ts, kernel, extra, dt):
     assert rc == 0, out + err
     assert "eMax:0.000e+00|eL1:0.000e+00-PASSED" in out
     assert out.startswith("#ts:" + ["Spatial Blocking", "Halo-first", "Diamond"][ts])
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_cli_verify_contracted(dt):
+    """--gpu-contract 1: the verifier (strict arithmetic) accepts on the north-star tolerance and the
+    error it reports is small but not zero"""
+    rc, out, err = G.run_reference_cli(dt, ["--nx", 48, "--ny", 32, "--nz", 40, "--nt", 20, "--target-ts", 2,
+                                            "--target-kernel", 1, "--t-dim", 3, "--verify", 1, "--verbose", 1,
+                                            "--gpu-contract", 1])
+    assert rc == 0, out + err
+    assert "-PASSED" in out and "eMax:0.000e+00" not in out
+    rel = float(re.search(r"relative Linf error: (\S+)", out).group(1))
+    assert 0 < rel <= TOL[np.dtype(dt)]
 
 
 def test_cli_performance_schema():

@@ -15,6 +15,9 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 SMALL = np.load(os.path.join(HERE, "golden", "small.npz"))
 SUMS = json.load(open(os.path.join(HERE, "golden", "checksums.json")))
+# the same cases from the reference built with FMA contraction (make_golden.py fma)
+SMALL_FMA = np.load(os.path.join(HERE, "golden", "small_fma.npz"))
+SUMS_FMA = json.load(open(os.path.join(HERE, "golden", "checksums_fma.json")))
 KEY = re.compile(r"k(\d)_(\d+)x(\d+)x(\d+)_nt(\d+)_ts(\d)_td(\d)_(sp|dp)$")
 
 
@@ -24,13 +27,13 @@ def parse(key):
     return k, (nx, ny, nz), nt, ts, td, (np.float32 if m.group(8) == "sp" else np.float64)
 
 
-def run_oracle(O, k, st, nt, ts, td, dt):
+def run_oracle(O, k, st, nt, ts, td, dt, contract=False):
     pb = O.make_problem(k, st, dt)
     if ts == 2:                      # diamond: nt rounded up, nt-1 steps executed
         nt = O.diamond_round_nt(nt, td)
-        O.run_steps(pb, nt - 1)
+        O.run_steps(pb, nt - 1, contract=contract)
     else:
-        O.run_naive(pb, nt)
+        O.run_naive(pb, nt, contract=contract)
     return pb, nt
 
 
@@ -43,6 +46,24 @@ def test_small_golden(oracle, key):
     assert gold.dtype == dt
     got = pb.interior()
     assert got.tobytes() == gold.tobytes()
+
+
+@pytest.mark.parametrize("key", sorted(k for k in SMALL_FMA.files if not k.endswith("_nteff")))
+def test_small_golden_contracted(oracle, key):
+    """The oracle compiled with gcc's FMA contraction == the reference compiled the same way."""
+    k, st, nt, ts, td, dt = parse(key)
+    pb, _ = run_oracle(oracle, k, st, nt, ts, td, dt, contract=True)
+    assert pb.interior().tobytes() == SMALL_FMA[key].tobytes()
+    assert SMALL_FMA[key].tobytes() != SMALL[key].tobytes()      # and it is a different rounding
+
+
+@pytest.mark.parametrize("key", sorted(SUMS_FMA))
+def test_checksum_golden_contracted(oracle, key):
+    k, st, nt, ts, td, dt = parse(key)
+    pb, nte = run_oracle(oracle, k, st, nt, ts, td, dt, contract=True)
+    assert nte == SUMS_FMA[key]["nt_effective"]
+    got = np.ascontiguousarray(pb.interior())
+    assert hashlib.sha256(got.tobytes()).hexdigest() == SUMS_FMA[key]["sha256"]
 
 
 @pytest.mark.parametrize("key", sorted(SUMS))

@@ -39,3 +39,33 @@ def test_reference_own_verify_passes(oracle):
                                       "--target-ts", 0, "--verify", 1, "--verbose", 0,
                                       "--thread-group-size", 2], threads=2)
     assert "eMax:0.000e+00|eL1:0.000e+00-PASSED" in out
+
+
+def _need_fast_ref(O):
+    import os
+    _need_ref(O)
+    if not os.path.exists(os.path.join(O.REF_DIR, "ref_dump_dp_fast")):
+        pytest.skip("oracle/_ref/ref_dump_*_fast not built")
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 3, 4, 5, 7])
+def test_contracted_oracle_equals_reference_built_with_fma(oracle, kernel, dt):
+    """oracle_*_{dpf,spf} (gcc -mfma -ffp-contract=fast) == the reference compiled with the same flags,
+    for the single-step stepper and (radius 1) the diamond stepper; and both differ from strict."""
+    _need_fast_ref(oracle)
+    st = (17, 12, 13)
+    U1, r, nte = oracle.ref_dump(kernel, st, 7, dt, ts=0, fast=True)
+    pb = oracle.make_problem(kernel, st, dt)
+    oracle.run_naive(pb, 7, contract=True)
+    assert U1.tobytes() == pb.U1.tobytes()
+    strict = oracle.make_problem(kernel, st, dt)
+    oracle.run_naive(strict, 7)
+    assert strict.U1.tobytes() != pb.U1.tobytes()
+    if r == 1:
+        st = (17, 16, 13)
+        U1, r, nte = oracle.ref_dump(kernel, st, 9, dt, ts=2, threads=1, fast=True,
+                                     extra=("--t-dim", 1, "--thread-group-size", 1, "--num-wavefronts", 1))
+        pb = oracle.make_problem(kernel, st, dt)
+        oracle.run_steps(pb, nte - 1, contract=True)
+        assert U1.tobytes() == pb.U1.tobytes()

@@ -14,16 +14,17 @@ ap.add_argument("--tfuse", type=int, default=1)
 ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--tile", type=int, default=0)
 ap.add_argument("--zchunk", type=int, default=0)
+ap.add_argument("--contract", type=int, default=0)
 a = ap.parse_args()
 st = tuple(int(x) for x in a.st.split(","))
 dt = np.float64 if a.dtype == "f64" else np.float32
 pb = G.make_problem(a.kernel, st, dt)
 s = G.GpuStepper.for_problem(pb)
-s.set_option("variant", a.variant); s.set_option("tile", a.tile); s.set_option("zchunk", a.zchunk)
+s.set_option("contract", a.contract); s.set_option("variant", a.variant); s.set_option("tile", a.tile); s.set_option("zchunk", a.zchunk)
 s.run_fused(a.nsteps, a.tfuse)
 s.download(pb.U1, pb.U2)
 ob = O.make_problem(a.kernel, st, dt)
-O.run_steps(ob, a.nsteps)
+O.run_steps(ob, a.nsteps, contract=bool(a.contract))
 for name, g, o in (("U1", pb.U1, ob.U1), ("U2", pb.U2, ob.U2)):
     bad = np.argwhere(g != o)
     print(name, "mismatches:", len(bad), "of", g.size)

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--zchunks", default="0")
     ap.add_argument("--variants", default="0")
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--contract", type=int, default=0)
     a = ap.parse_args()
     n = a.n
     for k in [int(x) for x in a.kernels.split(",")]:
@@ -36,6 +37,7 @@ def main():
             dt = np.float64 if dn == "f64" else np.float32
             pb = G.make_problem(k, (n, n, n), dt)
             s = G.GpuStepper.for_problem(pb)
+            s.set_option("contract", a.contract)
             for variant in [int(x) for x in a.variants.split(",")]:
                 s.set_option("variant", variant)
                 for tile in [int(x) for x in a.tiles.split(",")]:
