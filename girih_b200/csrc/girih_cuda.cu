@@ -544,9 +544,11 @@ static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb
 // every fused level, so the gain shrinks (slot 2, 3) or vanishes (slot 5: 9 words per update).
 static int default_tfuse(const girih_gpu_ctx *c) {
   switch (c->kernel) {
+    // fastest measured depth per (operator, precision) at 512^3, profiles/kernel_sweep_r01.md
     case 1: return 4;
-    case 2: return 3;
-    case 3: return c->es == 8 ? 2 : 3;
+    case 2: return c->es == 8 ? 2 : 3;
+    case 3: return c->es == 8 ? 1 : 2;
+    case 5: return c->es == 8 ? 1 : 2;
     default: return 1;
   }
 }

@@ -128,7 +128,16 @@ k_r1(const R1Args<R> a) {
   }
   // warps that lie completely inside the domain skip the per-point pass-through fix-up
   const bool warp_masked = __any_sync(0xffffffffu, interior_xy != ALL);
+  unsigned full_rows = 0, part_rows = 0;   // rows stored whole / rows stored point by point
+#pragma unroll
+  for (int j = 0; j < PY; ++j) {
+    const unsigned m = (core_xy >> (j * VX)) & ((1u << VX) - 1u);
+    if (m == (1u << VX) - 1u) full_rows |= 1u << j;
+    else if (m != 0u) part_rows |= 1u << j;
+  }
+  const bool any_part = __any_sync(0xffffffffu, part_rows != 0u);
   const long long row0 = (long long)y0 * g.px + x;   // offset of my first point inside a plane
+  const R *const coef_t = a.coef + row0;   // per-thread base; the (z, row) offset below is warp-uniform
   const int nit = (ze - zb) + 2 * T;
 
   // The loop body exists twice: FRAME = false for iterations in which this warp cannot see a
@@ -161,13 +170,14 @@ k_r1(const R1Args<R> a) {
 #pragma unroll
       for (int e = 0; e < VX; ++e) nxt[q][j][e] = (R)0;
 
-  auto load_plane = [&](int z, R (&dst)[PY][VX]) {
-    if ((z >= 0) && (z < g.nz_dev)) {
-      const R *p = a.in + (long long)z * g.pxy + row0;
+  // branch-free (predicated loads): the fused levels stay one basic block, so the scheduler can run
+  // one level's arithmetic under another level's shuffle / shared-memory latency
+  auto load_plane = [&](int z, R (&dst)[PY][VX], bool want = true) {
+    const unsigned m = (want && (z >= 0) && (z < g.nz_dev)) ? row_alloc : 0u;
+    const R *p = a.in + (long long)z * g.pxy + row0;
 #pragma unroll
-      for (int j = 0; j < PY; ++j)
-        if ((row_alloc >> j) & 1u) ld128<R>(p + (long long)j * g.px, dst[j]);
-    }
+    for (int j = 0; j < PY; ++j)
+      if ((m >> j) & 1u) ld128<R>(p + (long long)j * g.px, dst[j]);
   };
   if constexpr (T == 1) {
 #pragma unroll
@@ -196,7 +206,7 @@ k_r1(const R1Args<R> a) {
         for (int j = 0; j < PY; ++j)
 #pragma unroll
           for (int e = 0; e < VX; ++e) nxt[q][j][e] = nxt[q + 1][j][e];
-      if (it + PF < nit) load_plane(zin + PF, nxt[PF - 1]);
+      load_plane(zin + PF, nxt[PF - 1], it + PF < nit);
     }
 
     // publish the first/last row of the level-0 plane for next iteration's level-1 update
@@ -234,7 +244,7 @@ k_r1(const R1Args<R> a) {
         R cf[NCA > 0 ? NCA : 1][VX];
         if constexpr (NCA > 0) {
           const bool ok = (zc >= 0) && (zc < g.nz_dev) && ((row_alloc >> j) & 1u);
-          const R *cp = a.coef + (long long)zc * g.pxy + row0 + (long long)j * g.px;
+          const R *cp = coef_t + ((long long)zc * g.pxy + (long long)j * g.px);
 #pragma unroll
           for (int m = 0; m < NCA; ++m) {
 #pragma unroll
@@ -281,20 +291,25 @@ k_r1(const R1Args<R> a) {
       if constexpr (l + 1 < T) stage(S[l + 1][iF]);
       else stage(Ofin);
       if constexpr (T > 1 && l == 0) {
-        if (it + 1 < nit) load_plane(zin + 1, S[0][iB]);   // next iteration's level-0 "F"
+        load_plane(zin + 1, S[0][iB], it + 1 < nit);   // next iteration's level-0 "F"
       }
     });
 
-    // Ofin is level T at plane zin - T
+    // Ofin is level T at plane zin - T.  Rows whose VX points all lie in the core go out as predicated
+    // 128-bit stores (no branches); rows cut by the domain edge (nx not a multiple of VX) are rare and
+    // take a warp-uniform slow path.
     const int zo = zin - T;
-    if (zo >= zb && zo < ze) {
-      R *q = a.out + (long long)zo * g.pxy + row0;
+    const bool zst = (zo >= zb) && (zo < ze);
+    R *q = a.out + (long long)zo * g.pxy + row0;
+    const unsigned fm = zst ? full_rows : 0u;
+#pragma unroll
+    for (int j = 0; j < PY; ++j)
+      if ((fm >> j) & 1u) st128<R>(q + (long long)j * g.px, Ofin[j]);
+    if (any_part && zst) {
 #pragma unroll
       for (int j = 0; j < PY; ++j) {
-        const unsigned m = (core_xy >> (j * VX)) & ((1u << VX) - 1u);
-        if (m == (1u << VX) - 1u) {
-          st128<R>(q + (long long)j * g.px, Ofin[j]);
-        } else if (m != 0u) {
+        if ((part_rows >> j) & 1u) {
+          const unsigned m = (core_xy >> (j * VX)) & ((1u << VX) - 1u);
 #pragma unroll
           for (int e = 0; e < VX; ++e)
             if ((m >> e) & 1u) q[(long long)j * g.px + e] = Ofin[j][e];
