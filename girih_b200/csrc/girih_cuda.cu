@@ -508,7 +508,7 @@ static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb
   // variant 0 picks the fastest measured single-step kernel per operator and precision
   // (profiles/kernel_sweep_r01.md): the marching kernel, except for the fp64 variable-coefficient
   // operators where one thread per site with all loads in flight runs at the HBM limit already.
-  bool naive = (c->opt_variant == 1) || (c->kernel == 7);
+  bool naive = (c->opt_variant == 1);
   if (c->opt_variant == 0 && T == 1 && c->es == 8 && (c->kernel == 2 || c->kernel == 3 || c->kernel == 5)) naive = true;
   if (naive) {
     if (T != 1) return cudaErrorInvalidValue;
@@ -530,6 +530,7 @@ static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb
   sl.contract = c->opt_contract;
   sl.stream = c->s_comp;
   c->n_kernels++;
+  if (c->kernel == 7) return T == 1 ? launch_box(c->es, sl) : cudaErrorInvalidValue;
   if (g.r == 1) return launch_r1(c->kernel, c->es, T, sl);
   if (T != 1) return cudaErrorInvalidValue;
   return launch_r4(c->kernel, c->es, sl);

@@ -1,0 +1,41 @@
+// instantiation unit: 27-point box operator (slot 7), both precisions
+#include <algorithm>
+
+#include "kernels_box.cuh"
+#include "launch.h"
+
+namespace girih {
+
+template <typename R, int NW, bool FM>
+static cudaError_t launch_box_t(const StreamLaunch &s) {
+  const DevGrid &g = s.g;
+  constexpr int WX = 32 * Vec<R>::N;
+  BoxArgs<R> a;
+  a.g = g;
+  a.in = (const R *)s.in;
+  a.out = (R *)s.out;
+  for (int i = 0; i < 5; ++i) a.cc.v[i] = (R)s.cc[i];
+  a.zb0 = s.zb0;
+  a.ze0 = s.ze0;
+  const int nz = s.ze0 - s.zb0;
+  const int ntiles = ((g.nx + WX - 1) / WX) * ((g.ny + NW - 1) / NW);
+  int zchunk = s.zchunk > 0 ? s.zchunk : 64;
+  if (s.zchunk <= 0) {   // every chunk re-reads two planes; keep chunks long but leave several waves of CTAs
+    while (zchunk < nz && (long long)ntiles * ((nz + zchunk - 1) / zchunk) > 148LL * 8 * 8) zchunk *= 2;
+    while (zchunk > 16 && (long long)ntiles * ((nz + zchunk - 1) / zchunk) < 148LL * 8 * 2) zchunk /= 2;
+  }
+  zchunk = std::min(zchunk, std::max(nz, 1));
+  a.zchunk = zchunk;
+  dim3 grid((g.nx + WX - 1) / WX, (g.ny + NW - 1) / NW, (nz + zchunk - 1) / zchunk);
+  k_box_march<R, NW, FM><<<grid, 32 * NW, 0, s.stream>>>(a);
+  return cudaGetLastError();
+}
+
+// tile option = warps (rows) per CTA: 4 or 8 (default)
+cudaError_t launch_box(int es, const StreamLaunch &s) {
+  if (s.contract) return es == 8 ? launch_box_t<double, 8, true>(s) : launch_box_t<float, 8, true>(s);
+  if (s.tile == 4) return es == 8 ? launch_box_t<double, 4, false>(s) : launch_box_t<float, 4, false>(s);
+  return es == 8 ? launch_box_t<double, 8, false>(s) : launch_box_t<float, 8, false>(s);
+}
+
+}  // namespace girih

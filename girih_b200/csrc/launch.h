@@ -27,5 +27,7 @@ struct StreamLaunch {
 cudaError_t launch_r1(int kernel, int es, int T, const StreamLaunch &a);
 // one step of a radius-4 operator (slots 0, 4)
 cudaError_t launch_r4(int kernel, int es, const StreamLaunch &a);
+// one step of the 27-point box operator (slot 7)
+cudaError_t launch_box(int es, const StreamLaunch &a);
 
 }  // namespace girih
