@@ -206,6 +206,14 @@ class GpuStepper:
     def set_option(self, key, value):
         self._check(self._lib.girih_gpu_set_option(self._ctx, key.encode(), int(value)), "girih_gpu_set_option")
 
+    def autotune(self, fused=True, verbose=False):
+        """on-device search over fusion depth and tiles; returns (tfuse, tile, MLUP/s).  The fields evolve
+        while it measures: upload again before a run whose result matters."""
+        t, tile, perf = C.c_int(), C.c_int(), C.c_double()
+        self._check(self._lib.girih_gpu_autotune(self._ctx, int(fused), int(verbose), C.byref(t), C.byref(tile),
+                                                 C.byref(perf)), "girih_gpu_autotune")
+        return t.value, tile.value, perf.value
+
     def time_pass(self, tfuse, reps=10):
         """average device milliseconds of one fused pass (= one kernel launch)"""
         ms = C.c_double()

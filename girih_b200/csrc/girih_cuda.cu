@@ -88,6 +88,8 @@ struct girih_gpu_ctx {
   // accounting of the last run
   double ms_compute = 0, ms_comm = 0, ms_total = 0;
   int n_kernels = 0, n_passes = 0, n_steps = 0, tfuse_used = 1;
+  int tuned_tile[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // per fusion depth, set by girih_gpu_autotune (0 = built-in default)
+  int tuned_tfuse = 0;                            // 0 = built-in default depth
   unsigned long long *d_scan = nullptr;
   void *d_stage = nullptr;            // linear copy of one host array (fast-path transfers)
   char err[512] = "";
@@ -525,7 +527,7 @@ static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb
   sl.zb0 = zb0;
   sl.ze0 = ze0;
   sl.zchunk = c->opt_zchunk;
-  sl.tile = c->opt_tile;
+  sl.tile = c->opt_tile ? c->opt_tile : c->tuned_tile[T & 7];
   sl.variant = c->opt_variant;
   sl.contract = c->opt_contract;
   sl.stream = c->s_comp;
@@ -703,7 +705,7 @@ extern "C" int girih_gpu_run_single(girih_gpu_ctx *c, int nsteps, int overlap) {
 extern "C" int girih_gpu_run_fused(girih_gpu_ctx *c, int nsteps, int tfuse) {
   if (!c || nsteps < 0) return GIRIH_ERR_ARG;
   int T = tfuse;
-  if (T <= 0) T = default_tfuse(c);
+  if (T <= 0) T = c->tuned_tfuse > 0 ? c->tuned_tfuse : default_tfuse(c);
   T = std::min(T, c->kd.max_tfuse);
   if (c->opt_variant == 1 || c->kernel == 7) T = 1;
   if (c->nranks > 1) T = std::min(T, std::max(1, c->g.nz / std::max(1, c->g.r)));
@@ -736,10 +738,8 @@ extern "C" int girih_gpu_step_box(girih_gpu_ctx *c, int dst, int xb, int yb, int
   return GIRIH_OK;
 }
 
-extern "C" int girih_gpu_time_pass(girih_gpu_ctx *c, int tfuse, int reps, double *ms_per_pass) {
-  if (!c || reps < 1 || !ms_per_pass) return GIRIH_ERR_ARG;
-  if (!c->uploaded) return fail(c, GIRIH_ERR_STATE, "time_pass before upload");
-  if (c->nranks != 1) return fail(c, GIRIH_ERR_ARG, "time_pass works on single-slab contexts");
+// `reps` passes of depth tfuse over this slab's interior planes, no halo exchange
+static int time_pass_local(girih_gpu_ctx *c, int tfuse, int reps, double *ms_per_pass) {
   int T = std::max(1, std::min(tfuse, c->kd.max_tfuse));
   if (c->opt_variant == 1 || c->kernel == 7) T = 1;
   if (T > 1 && !c->frames_equal) return fail(c, GIRIH_ERR_FRAME, "%s", girih_gpu_strerror(GIRIH_ERR_FRAME));
@@ -761,6 +761,87 @@ extern "C" int girih_gpu_time_pass(girih_gpu_ctx *c, int tfuse, int reps, double
   *ms_per_pass = (double)ms / reps;
   c->tfuse_used = T;
   return GIRIH_OK;
+}
+
+extern "C" int girih_gpu_time_pass(girih_gpu_ctx *c, int tfuse, int reps, double *ms_per_pass) {
+  if (!c || reps < 1 || !ms_per_pass) return GIRIH_ERR_ARG;
+  if (!c->uploaded) return fail(c, GIRIH_ERR_STATE, "time_pass before upload");
+  if (c->nranks != 1) return fail(c, GIRIH_ERR_ARG, "time_pass works on single-slab contexts");
+  return time_pass_local(c, tfuse, reps, ms_per_pass);
+}
+
+// ------------------------------------------------------------------------------------------------
+// on-device tuner: the GPU analogue of auto_tune_params (src/kernels/diamond_utils.c:691-847) --
+// measure every (fusion depth, tile) this operator has kernels for on the resident slab, keep the
+// fastest, report under the reference's "[AUTO TUNE]" prefix.  The fields evolve while measuring:
+// the caller uploads them again afterwards.
+// ------------------------------------------------------------------------------------------------
+static std::vector<int> tile_candidates(const girih_gpu_ctx *c, int T) {
+  if (c->opt_variant == 1) return {0};
+  if (c->kernel == 7) return {0, 4};
+  if (c->kernel == 0) return {0, 8, 16, 116};
+  if (c->kernel == 4) return {0, 8, 16};
+  if (T == 1) {
+    if (c->opt_variant == 0 && c->es == 8 && (c->kernel == 2 || c->kernel == 3 || c->kernel == 5)) return {0};
+    if (c->opt_variant == 2) return {216, 408};
+    return {0, 108, 208, 404, 408};
+  }
+  if (c->opt_contract) return {0};
+  if (c->kernel == 1) return {216, 408, 312, 310, 316};
+  return {216, 408};
+}
+
+extern "C" int girih_gpu_autotune(girih_gpu_ctx *c, int fused, int verbose, int *best_tfuse, int *best_tile,
+                                  double *best_mlups) {
+  if (!c) return GIRIH_ERR_ARG;
+  if (!c->uploaded) return fail(c, GIRIH_ERR_STATE, "autotune before upload");
+  const int saved_tile = c->opt_tile;
+  const double lups = (double)c->g.nx * c->g.ny * c->g.nz;
+  int Tmax = fused ? c->kd.max_tfuse : 1;
+  if (c->opt_variant == 1 || c->kernel == 7 || !c->frames_equal) Tmax = 1;
+  if (c->nranks > 1) Tmax = std::min(Tmax, std::max(1, c->g.nz / std::max(1, c->g.r)));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, c->s_comp));
+  double best = -1;
+  int bT = 1, rc = GIRIH_OK;
+  if (verbose) printf("[AUTO TUNE] GPU kernels of operator %d (%s): fusion depth 1..%d, tiles per depth\n", c->kernel,
+                      c->es == 8 ? "fp64" : "fp32", Tmax);
+  for (int T = 1; T <= Tmax && rc == GIRIH_OK; ++T) {
+    double bestT = -1;
+    int btile = 0;
+    for (int tile : tile_candidates(c, T)) {
+      c->opt_tile = tile;
+      double ms = 0;
+      rc = time_pass_local(c, T, 3, &ms);
+      if (rc != GIRIH_OK) break;
+      const double mlups = lups * T / ms / 1e3;
+      if (verbose) printf("[AUTO TUNE]     [T:%d tile:%04d]  time:%e  MLUPS:%06llu\n", T, tile, ms * 1e-3, (unsigned long long)mlups);
+      if (mlups > bestT) { bestT = mlups; btile = tile; }
+    }
+    c->tuned_tile[T & 7] = btile;
+    if (bestT > best) { best = bestT; bT = T; }
+  }
+  c->opt_tile = saved_tile;
+  if (rc == GIRIH_OK) {
+    c->tuned_tfuse = bT;
+    CU(cudaEventRecord(e1, c->s_comp));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (verbose) {
+      printf("[AUTO TUNE] COMPLETE: fused steps per pass:%d  tile:%04d  perf:%7.2f MLUP/s\n", bT, c->tuned_tile[bT & 7], best);
+      printf("[AUTO TUNE]  Tuning time: %5.3f seconds\n", ms * 1e-3);
+      fflush(stdout);
+    }
+    if (best_tfuse) *best_tfuse = bT;
+    if (best_tile) *best_tile = c->tuned_tile[bT & 7];
+    if (best_mlups) *best_mlups = best;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
 }
 
 extern "C" int girih_gpu_last_elapsed_ms(girih_gpu_ctx *c, double *compute_ms, double *comm_ms, double *total_ms) {

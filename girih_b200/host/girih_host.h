@@ -62,6 +62,7 @@ typedef struct Parameters {
   int gpu_tfuse;                    /* --gpu-tfuse: fused steps per HBM pass for ts 2 (0 = auto) */
   int gpu_variant;                  /* --gpu-variant: 0 auto, 1 naive kernels */
   int gpu_overlap;                  /* --gpu-overlap: overlap halo exchange with compute */
+  int gpu_tune;                     /* --gpu-tune: on-device search over fusion depth and tiles ([AUTO TUNE]) */
   int gpu_contract;                 /* --gpu-contract: FMA-contracted arithmetic (reference built with -mfma) */
   /* decomposition */
   int mpi_rank, mpi_size;

@@ -314,6 +314,18 @@ void gpu_attach(Parameters *p) {
   gpu_check(p, girih_gpu_set_option(p->gpu, "overlap", p->gpu_overlap), "girih_gpu_set_option");
   gpu_check(p, girih_gpu_set_option(p->gpu, "contract", p->gpu_contract), "girih_gpu_set_option");
   gpu_check(p, girih_gpu_upload(p->gpu, p->U1, p->U2, p->U3, p->coef), "girih_gpu_upload");
+  if (p->gpu_tune) {
+    /* like the reference's auto-tuner this runs before the measured tests; the fields it advanced are
+     * uploaded again.  Every rank tunes its own slab; rank 0 prints. */
+    int bt = 0;
+    gpu_check(p, girih_gpu_autotune(p->gpu, p->target_ts == 2 && p->gpu_tfuse <= 0, p->mpi_rank == 0 && p->verbose, &bt, NULL, NULL),
+              "girih_gpu_autotune");
+    if (p->target_ts == 2 && p->gpu_tfuse <= 0) { /* all slabs must run the same pass schedule: rank 0 decides */
+      team_bcast(&bt, sizeof(bt), 0, p->mpi_rank);
+      p->gpu_tfuse = bt;
+    }
+    gpu_check(p, girih_gpu_upload(p->gpu, p->U1, p->U2, p->U3, p->coef), "girih_gpu_upload");
+  }
 }
 
 void gpu_detach(Parameters *p) {

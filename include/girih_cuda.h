@@ -188,6 +188,15 @@ int girih_gpu_scan_u1(girih_gpu_ctx *ctx, uint64_t *n_nan_inf, uint64_t *n_zero)
  *              instructions per lattice update.  With 1 the "tile" option is ignored (default tiles). */
 int girih_gpu_set_option(girih_gpu_ctx *ctx, const char *key, int value);
 
+/* On-device tuner -- the GPU analogue of auto_tune_params() (src/kernels/diamond_utils.c:691-847, the
+ * "measure every feasible blocking, keep the fastest" loop of run_tuning_test, :244-269): times every
+ * (fused steps per pass, tile) this operator has kernels for on the resident slab and keeps the fastest for
+ * later run_single / run_fused(tfuse = 0) calls of this context.  fused = 0 tunes the single-step pass only.
+ * verbose = 1 prints the candidates under the reference's "[AUTO TUNE]" prefix on stdout.  The fields keep
+ * evolving while it measures: upload them again afterwards.  Outputs may be NULL. */
+int girih_gpu_autotune(girih_gpu_ctx *ctx, int fused, int verbose, int *best_tfuse, int *best_tile,
+                       double *best_mlups);
+
 const char *girih_gpu_strerror(int status);
 /* Detail of the last failure on this context (CUDA/NCCL error string); never NULL. */
 const char *girih_gpu_last_error(girih_gpu_ctx *ctx);

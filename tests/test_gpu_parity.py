@@ -235,6 +235,15 @@ def test_radius4_tile_seams(oracle, kernel, dt):
             assert_same(pb, ob)
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("opts", [(), (("tile", 4),), (("contract", 1),), (("zchunk", 5),)])
+def test_box_kernel_tile_seams(oracle, dt, opts):
+    """slot 7 streamed kernel: several warps / CTAs in x and y, ragged extents, short z chunks"""
+    for st in ((150, 71, 23), (130, 9, 40), (3, 2, 2)):
+        pb, _, _ = gpu_run(7, st, dt, 0, 6, options=opts)
+        assert_same(pb, oracle_run(oracle, 7, st, dt, 0, 6, contract=(("contract", 1) in opts)))
+
+
 @pytest.mark.parametrize("kernel", [0, 1, 2, 3, 4, 5, 7])
 def test_naive_variant_and_edge_sizes(oracle, kernel):
     """tiny and degenerate domains (1 cell wide), naive kernels vs streamed kernels vs oracle"""
@@ -361,6 +370,32 @@ def test_cli_verify_contracted(dt):
     assert "-PASSED" in out and "eMax:0.000e+00" not in out
     rel = float(re.search(r"relative Linf error: (\S+)", out).group(1))
     assert 0 < rel <= TOL[np.dtype(dt)]
+
+
+def test_autotune_then_results_are_unchanged(oracle):
+    """the tuner picks a depth/tile; after re-uploading, a tuned run is bit-identical to the oracle"""
+    st = (150, 71, 40)
+    pb = G.make_problem(1, st, np.float64)
+    s = G.GpuStepper.for_problem(pb)
+    t, tile, perf = s.autotune(fused=True)
+    assert 1 <= t <= G.kernel_info(1).max_tfuse and perf > 0
+    s.upload(pb)
+    s.run_fused(11, 0)
+    assert s.launch_info()["tfuse"] == t
+    s.download(pb.U1, pb.U2)
+    s.close()
+    ob = oracle.make_problem(1, st, np.float64)
+    oracle.run_steps(ob, 11)
+    assert_same(pb, ob)
+
+
+def test_cli_autotune_prints_reference_prefix():
+    rc, out, err = G.run_reference_cli(np.float32, ["--nx", 96, "--ny", 64, "--nz", 64, "--nt", 20, "--target-ts", 2,
+                                                    "--target-kernel", 1, "--t-dim", 3, "--verify", 1,
+                                                    "--gpu-tune", 1])
+    assert rc == 0, out + err
+    assert "[AUTO TUNE] COMPLETE: fused steps per pass:" in out and "[AUTO TUNE]  Tuning time:" in out
+    assert "eMax:0.000e+00|eL1:0.000e+00-PASSED" in out
 
 
 def test_cli_performance_schema():
