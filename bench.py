@@ -201,7 +201,10 @@ def main_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
     torch.cuda.set_device(local)
-    os.environ["NCCL_DEBUG"] = os.environ.get("GIRIH_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+    # NCCL writes its banner ("NCCL version ...") and debug lines to stdout: send them to a file so that
+    # stdout carries exactly the one JSON line
+    os.environ["NCCL_DEBUG"] = os.environ.get("GIRIH_NCCL_DEBUG", "WARN")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/girih_bench_nccl_%h_%p.log")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -227,6 +230,7 @@ def main_ours(args):
     s.upload(pb)
     contract = int(args.arith == "contract")
     s.set_option("contract", contract)
+    s.set_option("overlap", int(args.overlap))
     if args.tfuse:
         tf = args.tfuse
     else:
@@ -242,14 +246,17 @@ def main_ours(args):
     if rank == 0:
         sampler.start()
     barrier()
-    dev_ms, launches = 0.0, 0
+    dev_ms, comm_ms, launches = 0.0, 0.0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         s.run_fused(nsteps, tf)
-        dev_ms += s.elapsed_ms()["total"]
+        el = s.elapsed_ms()
+        dev_ms += el["total"]
+        comm_ms += el["comm"]
         launches += s.launch_info()["kernels"]
     barrier()
     wall = time.perf_counter() - t0
+    comm_ms = allmax(comm_ms)
     clocks = sampler.stop() if rank == 0 else None
     dev_s = allmax(dev_ms * 1e-3)
     info = s.launch_info()
@@ -353,6 +360,9 @@ def main_ours(args):
                                  "strict: separate multiply/add, bit-exact vs the reference verifier (library default)"),
                        "parallelism": f"z-slab x{world}", "cache": "grid (2 x 1.1 GB per GPU) exceeds the 126 MB L2; no flush needed",
                        "timing": "cudaEvents on the launching stream inside the C ABI, max over ranks",
+                       "halo_exchange": (None if world == 1 else
+                                         {"ms_per_step_max_over_ranks": comm_ms / args.steps,
+                                          "overlap_with_interior": bool(args.overlap)}),
                        "wall_s": wall},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "GLUP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -372,6 +382,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tfuse", type=int, default=0)
+    ap.add_argument("--overlap", type=int, default=0, help="N>1: boundary planes first, exchange under the interior")
     ap.add_argument("--arith", default="strict", choices=["strict", "contract"],
                     help="strict = library default (no FMA); contract = FMA pattern of the reference built with -mfma")
     ap.add_argument("--ref-nz", type=int, default=512, help="z extent of the bounded CPU sample")

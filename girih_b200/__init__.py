@@ -7,7 +7,9 @@ and bench.py -- it contains no arithmetic and NO fallback: if the native librari
 import of girih_b200.lib raises, and without a CUDA device every stepper call raises GirihError.
 """
 from .api import (GirihError, GpuStepper, HostProblem, KernelDesc, diamond_nt, gpu_count,  # noqa: F401
-                  kernel_info, make_problem, plan_fused_passes, plan_halo_exchange, run_reference_cli)
+                  kernel_info, make_problem, plan_fused_exchanges, plan_fused_passes, plan_halo_exchange,
+                  run_reference_cli)
 
 __all__ = ["GirihError", "GpuStepper", "HostProblem", "KernelDesc", "diamond_nt", "gpu_count",
-           "kernel_info", "make_problem", "plan_fused_passes", "plan_halo_exchange", "run_reference_cli"]
+           "kernel_info", "make_problem", "plan_fused_exchanges", "plan_fused_passes", "plan_halo_exchange",
+           "run_reference_cli"]

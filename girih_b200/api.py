@@ -247,6 +247,16 @@ def plan_fused_passes(nsteps: int, tfuse: int) -> list:
     return list(buf[:n.value])
 
 
+def plan_fused_exchanges(nsteps: int, tfuse: int, r: int, halo_cap: int, group: int) -> list:
+    """halo planes exchanged before each pass of plan_fused_passes(nsteps, tfuse); 0 = no exchange (host-only)"""
+    n = C.c_int()
+    buf = (C.c_int * (nsteps + 4))()
+    rc = _lib.cuda().girih_plan_fused_exchanges(nsteps, tfuse, r, halo_cap, group, buf, nsteps + 4, C.byref(n))
+    if rc:
+        raise GirihError(rc, "girih_plan_fused_exchanges")
+    return list(buf[:n.value])
+
+
 def plan_halo_exchange(nz: int, depth: int, rank: int, nranks: int) -> dict:
     """first local plane of the send/recv blocks of one z exchange (host-only)"""
     v = [C.c_int() for _ in range(4)]

@@ -73,6 +73,8 @@ struct girih_gpu_ctx {
   DevGrid g{};
   size_t arr_elems = 0;
   int halo_max = 0;            // deepest z halo the allocation supports (planes)
+  int nz_min = 0;              // thinnest slab of the run (agreed at comm_init): every rank derives the same schedule
+  int opt_halo_group = 0;      // fused passes served by one exchange (0 = choose)
   void *dU[2] = {nullptr, nullptr};   // [0] = U1, [1] = U2
   void *dU3 = nullptr, *dCoef = nullptr;
   double cc[5] = {0, 0, 0, 0, 0};
@@ -161,17 +163,21 @@ extern "C" int girih_gpu_create(girih_gpu_ctx **out, int device, int target_kern
   g.r = r; g.nx = st[0]; g.ny = st[1]; g.nz = st[2];
   g.X0 = epl;                                 // >= guard, keeps x = X0 line aligned
   g.Y0 = std::max(guard, r);
-  g.Z0 = std::max(guard, r);
+  // z-slab runs keep up to 4 fused passes' worth of halo planes so that one exchange can serve several
+  // passes (run_passes); a single slab needs only the pipeline's own guard planes
+  const int zguard = std::max(guard, r) * (nranks > 1 ? 4 : 1);
+  g.Z0 = zguard;
   g.px = round_up(g.X0 + g.nx + std::max(guard, r), epl) + epl;
   g.ny_dev = g.Y0 + g.ny + std::max(guard, r);
-  g.nz_dev = g.Z0 + g.nz + std::max(guard, r);
+  g.nz_dev = g.Z0 + g.nz + zguard;
   g.pxy = (long long)g.px * g.ny_dev;
   g.zlo = (rank == 0) ? g.Z0 : -(1 << 30);
   g.zhi = (rank == nranks - 1) ? g.Z0 + g.nz : (1 << 30);
-  c->halo_max = std::max(guard, r);
+  c->halo_max = (nranks > 1) ? std::min(zguard, std::max(g.nz, std::max(guard, r))) : zguard;
+  c->nz_min = g.nz;
   c->arr_elems = (size_t)g.pxy * g.nz_dev;
-  if (nranks > 1 && g.nz < c->halo_max) {
-    fail(c, GIRIH_ERR_ARG, "slab of %d planes is thinner than the deepest halo (%d)", g.nz, c->halo_max);
+  if (nranks > 1 && g.nz < std::max(guard, r)) {
+    fail(c, GIRIH_ERR_ARG, "slab of %d planes is thinner than the deepest halo (%d)", g.nz, std::max(guard, r));
     return bail(GIRIH_ERR_ARG);
   }
 
@@ -191,7 +197,11 @@ extern "C" int girih_gpu_create(girih_gpu_ctx **out, int device, int target_kern
   }
   if (e == cudaSuccess) e = cudaMalloc(&c->d_scan, 2 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking);
+  if (e == cudaSuccess) {   // the exchange stream outranks the sweep: its few CTAs go first when SM slots free up
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    e = cudaStreamCreateWithPriority(&c->s_comm, cudaStreamNonBlocking, hi);
+  }
   if (e == cudaSuccess) e = cudaEventCreate(&c->ev_t0);
   if (e == cudaSuccess) e = cudaEventCreate(&c->ev_t1);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming);
@@ -233,6 +243,7 @@ extern "C" int girih_gpu_set_option(girih_gpu_ctx *c, const char *key, int value
   else if (!strcmp(key, "tile")) c->opt_tile = value;
   else if (!strcmp(key, "overlap")) c->opt_overlap = value;
   else if (!strcmp(key, "contract")) c->opt_contract = (value != 0);
+  else if (!strcmp(key, "halo_group")) c->opt_halo_group = value;
   else return fail(c, GIRIH_ERR_ARG, "unknown option '%s'", key);
   return GIRIH_OK;
 }
@@ -402,6 +413,13 @@ extern "C" int girih_gpu_comm_init(girih_gpu_ctx *c, const void *id, size_t len)
   ncclUniqueId uid;
   memcpy(&uid, id, sizeof(uid));
   NC(nccl_dyn()->CommInitRank(&c->comm, c->nranks, uid, c->rank));
+  // the thinnest slab bounds every halo depth; all ranks must derive the same exchange schedule from it
+  int *d_nz = reinterpret_cast<int *>(c->d_scan);
+  CU(cudaMemcpyAsync(d_nz, &c->g.nz, sizeof(int), cudaMemcpyHostToDevice, c->s_comm));
+  NC(nccl_dyn()->AllReduce(d_nz, d_nz + 1, 1, ncclInt32, ncclMin, c->comm, c->s_comm));
+  CU(cudaMemcpyAsync(&c->nz_min, d_nz + 1, sizeof(int), cudaMemcpyDeviceToHost, c->s_comm));
+  CU(cudaStreamSynchronize(c->s_comm));
+  c->halo_max = std::min(c->g.Z0, std::max(c->nz_min, c->g.r));
   return GIRIH_OK;
 }
 
@@ -504,9 +522,18 @@ static cudaError_t launch_naive(girih_gpu_ctx *c, int dst, int xb, int yb, int z
 
 // One fused pass: T steps reading array `src` and writing array `dst` (src != dst) on the output
 // planes [zb0, ze0) (device z).  T == 1 is the single step of ts 0/1.
-static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb0, int ze0) {
+// A second range [zb1, ze1) is swept by the same launch where the kernel supports it (fused r = 1 sweep),
+// else by a second launch.
+static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb0, int ze0, int zb1 = 0, int ze1 = 0) {
   const DevGrid &g = c->g;
   if (ze0 <= zb0) return cudaSuccess;
+  if (ze1 > zb1) {
+    const bool fused_kernel = (g.r == 1) && (c->kernel != 7) && (c->opt_variant != 1) && (T > 1 || c->opt_variant == 2);
+    if (!fused_kernel) {
+      cudaError_t e = launch_pass(c, T, src, dst, zb0, ze0);
+      return e != cudaSuccess ? e : launch_pass(c, T, src, dst, zb1, ze1);
+    }
+  }
   // variant 0 picks the fastest measured single-step kernel per operator and precision
   // (profiles/kernel_sweep_r01.md): the marching kernel, except for the fp64 variable-coefficient
   // operators where one thread per site with all loads in flight runs at the HBM limit already.
@@ -526,6 +553,8 @@ static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb
   for (int i = 0; i < 5; ++i) sl.cc[i] = c->cc[i];
   sl.zb0 = zb0;
   sl.ze0 = ze0;
+  sl.zb1 = zb1;
+  sl.ze1 = ze1;
   sl.zchunk = c->opt_zchunk;
   sl.tile = c->opt_tile ? c->opt_tile : c->tuned_tile[T & 7];
   sl.variant = c->opt_variant;
@@ -588,22 +617,97 @@ static int end_run(girih_gpu_ctx *c) {
 // overlap: the planes the neighbours need for the NEXT pass are computed first and their exchange
 // runs on the comm stream underneath the rest of the pass (the halo-first pattern,
 // src/kernels/halo_first_ts.c:156-194, with depth T*r instead of r).
+static void plan_passes(int nsteps, int T, std::vector<int> &sizes);
+
+// Exchange schedule of a run: depth[p] = halo planes exchanged before pass p (0 = none).  One exchange can
+// serve up to `group` consecutive passes: it brings depth = sum of their T*r planes, and every pass but the
+// last of the group also computes the planes of the neighbour's slab that the following passes will read
+// (the same deep-halo recomputation a fused pass does for its own T levels), so fewer, larger messages and
+// fewer points where the slabs wait for each other.
+static void plan_exchanges(const std::vector<int> &sizes, int r, int cap, int group, std::vector<int> &depth) {
+  depth.assign(sizes.size(), 0);
+  int ready = 0;
+  for (size_t p = 0; p < sizes.size(); ++p) {
+    const int need = sizes[p] * r;
+    if (ready < need) {
+      int D = need, cnt = 1;
+      for (size_t q = p + 1; q < sizes.size() && cnt < group && D + sizes[q] * r <= cap; ++q, ++cnt) D += sizes[q] * r;
+      depth[p] = D;
+      ready = D;
+    }
+    ready -= need;
+  }
+}
+
+extern "C" int girih_plan_fused_exchanges(int nsteps, int tfuse, int r, int halo_cap, int group, int *depth,
+                                          int max_n, int *n) {
+  if (nsteps < 0 || tfuse < 1 || r < 1 || halo_cap < tfuse * r || group < 1 || !n) return GIRIH_ERR_ARG;
+  std::vector<int> sizes, d;
+  plan_passes(nsteps, tfuse, sizes);
+  plan_exchanges(sizes, r, halo_cap, group, d);
+  *n = (int)d.size();
+  if (depth) {
+    if ((int)d.size() > max_n) return GIRIH_ERR_ARG;
+    for (size_t i = 0; i < d.size(); ++i) depth[i] = d[i];
+  }
+  return GIRIH_OK;
+}
+
+// passes served by one exchange: the option, else up to 4 while the recomputed planes stay a small
+// fraction of the thinnest slab
+static int halo_group(const girih_gpu_ctx *c, int T, bool overlap) {
+  if (c->nranks == 1 || overlap || c->kd.time_order != 1) return 1;
+  if (c->opt_halo_group > 0) return c->opt_halo_group;
+  int k = 1;
+  while (k < 4 && (k + 1) * T * c->g.r <= c->halo_max && k * T * c->g.r * 16 <= c->nz_min) ++k;
+  return k;
+}
+
 static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur, bool overlap) {
   const DevGrid &g = c->g;
   const int r = g.r;
   const int zb = g.Z0, ze = g.Z0 + g.nz;
   int ready = 0;   // depth of valid halo planes already present around array `cur`
   int rc;
+  int Tmax = 1;
+  for (int s : sizes) Tmax = std::max(Tmax, s);
+  const int group = halo_group(c, Tmax, overlap);
+  std::vector<int> depth;
+  plan_exchanges(sizes, r, c->halo_max, group, depth);
+  if (group > 1) {
+    // the Dirichlet frame cells of the deep-halo planes are never written by a kernel: bring them (with
+    // the planes) into BOTH arrays once; later exchanges and extended sweeps keep them
+    if ((rc = timed_exchange(c, c->dU[0], c->halo_max))) return rc;
+    if ((rc = timed_exchange(c, c->dU[1], c->halo_max))) return rc;
+  }
   for (size_t p = 0; p < sizes.size(); ++p) {
     const int T = sizes[p];
     const int src = cur, dst = cur ^ 1;
+    if (c->nranks > 1 && !overlap) {
+      if (depth[p] > 0) {
+        if ((rc = timed_exchange(c, c->dU[src], depth[p]))) return rc;
+        ready = depth[p];
+      }
+      // planes beyond the slab that later passes of this group read: computed here, towards neighbours only
+      const int ext = ready - T * r;
+      const int lo = (c->rank > 0) ? ext : 0, hi = (c->rank + 1 < c->nranks) ? ext : 0;
+      CU(launch_pass(c, T, src, dst, zb - lo, ze + hi));
+      ready = ext;
+      cur = dst;
+      c->n_passes++;
+      c->n_steps += T;
+      continue;
+    }
     if (c->nranks > 1 && ready < T * r) {
       if ((rc = timed_exchange(c, c->dU[src], T * r))) return rc;
     }
     const int nd = (p + 1 < sizes.size()) ? sizes[p + 1] * r : r;   // halo depth the next pass needs
     if (overlap && c->nranks > 1 && g.nz >= 4 * nd) {
-      CU(launch_pass(c, T, src, dst, zb, zb + nd));
-      CU(launch_pass(c, T, src, dst, ze - nd, ze));
+      // the two outer quarters of the slab first (one launch, full waves: thin boundary launches would pay
+      // the 2T-plane pipeline fill for a few planes), then the halo exchange of the new level runs under
+      // the sweep of the inner half
+      const int zq = std::max(nd, g.nz / 4);
+      CU(launch_pass(c, T, src, dst, zb, zb + zq, ze - zq, ze));
       CU(cudaEventRecord(c->ev_y, c->s_comp));
       CU(cudaStreamWaitEvent(c->s_comm, c->ev_y, 0));
       if (c->comm_ev_used == c->comm_ev.size()) {
@@ -616,7 +720,7 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
       CU(cudaEventRecord(q.a, c->s_comm));
       if ((rc = exchange_z(c, c->dU[dst], nd, c->s_comm))) return rc;
       CU(cudaEventRecord(q.b, c->s_comm));
-      CU(launch_pass(c, T, src, dst, zb + nd, ze - nd));
+      CU(launch_pass(c, T, src, dst, zb + zq, ze - zq));
       CU(cudaStreamWaitEvent(c->s_comp, q.b, 0));
       ready = nd;
     } else {

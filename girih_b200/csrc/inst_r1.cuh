@@ -41,7 +41,8 @@ static cudaError_t launch_r1_t(const StreamLaunch &s) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, 32 * NW, Cfg::SMEM) != cudaSuccess || occ < 1) occ = 1;
-    const int nz = s.ze0 - s.zb0, ntiles = ntx * nty, slots = nsm * occ;
+    // a second range of the same length doubles the CTAs per chunk row
+    const int nz = s.ze0 - s.zb0, ntiles = ntx * nty * (s.ze1 > s.zb1 ? 2 : 1), slots = nsm * occ;
     long long best = -1;
     zchunk = nz;
     for (int nch = 1; nch <= nz && nch <= 64; ++nch) {
@@ -54,7 +55,11 @@ static cudaError_t launch_r1_t(const StreamLaunch &s) {
     }
   }
   a.zchunk = zchunk;
-  dim3 grid(ntx, nty, (s.ze0 - s.zb0 + zchunk - 1) / zchunk);
+  a.nch0 = (s.ze0 - s.zb0 + zchunk - 1) / zchunk;
+  a.zb1 = s.zb1;
+  a.ze1 = s.ze1;
+  const int nch1 = (s.ze1 > s.zb1) ? (s.ze1 - s.zb1 + zchunk - 1) / zchunk : 0;
+  dim3 grid(ntx, nty, a.nch0 + nch1);
   kfn<<<grid, 32 * NW, Cfg::SMEM, s.stream>>>(a);
   return cudaGetLastError();
 }

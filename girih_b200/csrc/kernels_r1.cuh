@@ -36,6 +36,8 @@ template <typename R> struct R1Args {
   ConstCoef<R> cc;              // scalar coefficients (slot 1)
   int zb0, ze0;                 // output planes [zb0, ze0) of this launch (device z)
   int zchunk;                   // output planes per CTA
+  int nch0;                     // z chunks (blockIdx.z) that belong to [zb0, ze0); the rest cover a second
+  int zb1, ze1;                 // range [zb1, ze1): one launch can sweep the two outer parts of a slab
 };
 
 template <typename R, int T, int PY, int NW> struct R1Cfg {
@@ -100,8 +102,10 @@ k_r1(const R1Args<R> a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x = g.X0 - HX + (int)blockIdx.x * UX + lane * VX;   // my first column (device x)
   const int y0 = g.Y0 - T + (int)blockIdx.y * UY + warp * PY;   // my first row
-  const int zb = a.zb0 + (int)blockIdx.z * a.zchunk;
-  const int ze = min(zb + a.zchunk, a.ze0);
+  const int cz = (int)blockIdx.z;
+  const bool second = cz >= a.nch0;
+  const int zb = second ? a.zb1 + (cz - a.nch0) * a.zchunk : a.zb0 + cz * a.zchunk;
+  const int ze = min(zb + a.zchunk, second ? a.ze1 : a.ze0);
 
   // per-point facts that do not change along z
   const bool x_alloc = (x >= 0) && (x + VX <= g.px);

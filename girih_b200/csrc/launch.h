@@ -16,6 +16,7 @@ struct StreamLaunch {
   long long coef_stride;
   double cc[5];          // scalar coefficients
   int zb0, ze0;          // output planes [zb0, ze0), device z
+  int zb1, ze1;          // optional second range swept by the same launch (fused r = 1 sweep only), else 0, 0
   int zchunk;            // 0 = choose
   int tile;              // 0 = default, else PY*100 + NW
   int variant;           // 0 = auto, 2 = force the fused-sweep kernel also for T = 1

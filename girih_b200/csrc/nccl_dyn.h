@@ -14,6 +14,7 @@ struct NcclDyn {
   ncclResult_t (*CommDestroy)(ncclComm_t);
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
   ncclResult_t (*GroupStart)(void);
   ncclResult_t (*GroupEnd)(void);
   const char *(*GetErrorString)(ncclResult_t);
@@ -45,6 +46,7 @@ static inline NcclDyn *nccl_dyn() {
       SYM(CommDestroy, "ncclCommDestroy");
       SYM(Send, "ncclSend");
       SYM(Recv, "ncclRecv");
+      SYM(AllReduce, "ncclAllReduce");
       SYM(GroupStart, "ncclGroupStart");
       SYM(GroupEnd, "ncclGroupEnd");
       SYM(GetErrorString, "ncclGetErrorString");

@@ -17,7 +17,7 @@ ABI_SYMBOLS = [
     "girih_gpu_upload_fields", "girih_gpu_run_single", "girih_gpu_run_fused", "girih_gpu_step_box",
     "girih_gpu_time_pass", "girih_gpu_last_elapsed_ms", "girih_gpu_last_launch_info", "girih_gpu_scan_u1", "girih_gpu_set_option",
     "girih_gpu_autotune",
-    "girih_gpu_strerror", "girih_gpu_last_error", "girih_plan_fused_passes", "girih_plan_halo_exchange",
+    "girih_gpu_strerror", "girih_gpu_last_error", "girih_plan_fused_passes", "girih_plan_halo_exchange", "girih_plan_fused_exchanges",
 ]
 
 
@@ -60,6 +60,7 @@ def cuda() -> C.CDLL:
         lib.girih_gpu_set_option.argtypes = [P, C.c_char_p, I]
         lib.girih_gpu_autotune.argtypes = [P, I, I, C.POINTER(I), C.POINTER(I), C.POINTER(C.c_double)]
         lib.girih_plan_fused_passes.argtypes = [I, I, C.POINTER(I), I, C.POINTER(I)]
+        lib.girih_plan_fused_exchanges.argtypes = [I, I, I, I, I, C.POINTER(I), I, C.POINTER(I)]
         lib.girih_plan_halo_exchange.argtypes = [I, I, I, I] + [C.POINTER(I)] * 4
         lib.girih_gpu_strerror.argtypes = [I]
         lib.girih_gpu_strerror.restype = C.c_char_p

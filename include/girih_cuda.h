@@ -143,8 +143,12 @@ int girih_gpu_run_fused(girih_gpu_ctx *ctx, int nsteps, int tfuse);
  *                             single step that leaves U1/U2 as the reference does); sizes may be NULL
  *   girih_plan_halo_exchange  first plane of the four `depth`-plane blocks of one z exchange, in local
  *                             plane coordinates (0 = first interior plane); -1 / <-depth = no neighbour.
- *                             Geometry of src/mpi_utils.c:173-200 with depth = T*r instead of r. */
+ *                             Geometry of src/mpi_utils.c:173-200 with depth = T*r instead of r.
+ *   girih_plan_fused_exchanges  halo planes exchanged before each pass of that schedule (0 = none) when one
+ *                             exchange serves up to `group` passes and at most halo_cap planes: the first
+ *                             pass of a group also sweeps the neighbour's planes the later ones read. */
 int girih_plan_fused_passes(int nsteps, int tfuse, int *sizes, int max_sizes, int *n_sizes);
+int girih_plan_fused_exchanges(int nsteps, int tfuse, int r, int halo_cap, int group, int *depth, int max_n, int *n);
 int girih_plan_halo_exchange(int nz, int depth, int rank, int nranks, int *send_down, int *recv_down,
                              int *send_up, int *recv_up);
 
@@ -180,6 +184,8 @@ int girih_gpu_scan_u1(girih_gpu_ctx *ctx, uint64_t *n_nan_inf, uint64_t *n_zero)
  *   "tile"     fused sweep: PY*100 + NW (rows per thread, warps per CTA); marching kernel: rows per CTA
  *   "overlap"  fused passes: compute the slab boundaries first and overlap the deep-halo exchange with
  *              the interior (default 0: one exchange per pass, ordered before it, measured faster)
+ *   "halo_group" z-slab runs of first-order-in-time operators: fused passes served by one halo exchange
+ *              (0 = choose: up to 4 while the recomputed planes stay below 1/16 of the thinnest slab)
  *   "contract" arithmetic of the per-point expression.  0 (default): every product and sum rounded
  *              separately -- bit-identical to the reference built without FMA (conf/make.conf.gcc, `-O3`)
  *              and to its -O0 verifier (src/verification.c).  1: the fused multiply-adds gcc emits for the

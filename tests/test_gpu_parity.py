@@ -444,9 +444,10 @@ def test_z_slabs_match_global_oracle(oracle, kernel, tfuse):
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     gst, dt, nsteps = (40, 24, 16 * n + 3), np.float64, 11
-    for overlap in (0, 1):
+    for overlap, group in ((0, 0), (1, 0), (0, 3), (0, 4)):
         def fn(s):
             s.set_option("overlap", overlap)
+            s.set_option("halo_group", group)     # one exchange serves `group` passes (0 = choose)
             if tfuse == 1:
                 s.run_single(nsteps, overlap=bool(overlap))
             else:

@@ -46,18 +46,21 @@ def _exchange(arr, H, nz, depth, rank, nranks):
         arr[r0:r0 + depth] = recv.numpy()
 
 
-def _worker(rank, nranks, port, kernel, gst, dtname, nsteps, tfuse, q):
+def _worker(rank, nranks, port, kernel, gst, dtname, nsteps, tfuse, q, group=1):
     from oracle import girih_oracle as O
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=nranks)
     dt = np.dtype(dtname)
     info = G.kernel_info(kernel)
     r, T = info.r, min(tfuse, info.max_tfuse)
-    H = info.max_tfuse * r                      # the device allocation's halo_max
+    H = info.max_tfuse * r * 4                  # the device allocation's deepest halo (z-slab runs)
     pb = G.make_problem(kernel, gst, dt, rank=rank, nranks=nranks)
     nx, ny, nz = pb.stencil
     nnx, nny = pb.shape[0], pb.shape[1]
     first, last = rank == 0, rank == nranks - 1
+    t = torch.tensor([nz])                       # girih_gpu_comm_init: every rank derives depths from the
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)     # thinnest slab, so all schedules agree
+    hcap = min(info.max_tfuse * r * 4, max(int(t.item()), r))
 
     def deep(a):                                 # host array (r-deep z halo) -> deep-halo array
         d = np.zeros((nz + 2 * H, nny, nnx), dt)
@@ -71,14 +74,29 @@ def _worker(rank, nranks, port, kernel, gst, dtname, nsteps, tfuse, q):
     if info.n_coef_arrays:
         cd = np.stack([deep(pb.coef[m * ln:(m + 1) * ln].reshape(nz + 2 * r, nny, nnx)) for m in range(info.n_coef_arrays)])
         for m in range(info.n_coef_arrays):      # time-invariant arrays: deep halos once
-            _exchange(cd[m], H, nz, H, rank, nranks)
+            _exchange(cd[m], H, nz, hcap, rank, nranks)
         coef = np.ascontiguousarray(cd).reshape(-1)
     if U3 is not None:
-        _exchange(U3, H, nz, H, rank, nranks)
+        _exchange(U3, H, nz, hcap, rank, nranks)
     shape = (nnx, nny, nz + 2 * H)
     cur = 1                                      # level 0 is read from U2
-    for Tp in G.plan_fused_passes(nsteps, T):
-        _exchange(U[cur], H, nz, Tp * r, rank, nranks)
+    sizes = G.plan_fused_passes(nsteps, T)
+    # one exchange serves up to `group` passes (girih_plan_fused_exchanges, run_passes in girih_cuda.cu)
+    if info.time_order != 1:
+        group = 1
+    depths = G.plan_fused_exchanges(nsteps, T, r, hcap, group)
+    assert len(depths) == len(sizes)
+    if group > 1:                                # Dirichlet frame cells of the deep-halo planes, both arrays, once
+        _exchange(U[0], H, nz, hcap, rank, nranks)
+        _exchange(U[1], H, nz, hcap, rank, nranks)
+    ready = 0
+    for Tp, depth in zip(sizes, depths):
+        if depth:
+            _exchange(U[cur], H, nz, depth, rank, nranks)
+            ready = depth
+        assert ready >= Tp * r
+        more = ready - Tp * r                    # planes beyond the slab this pass must leave valid
+        ready = more
         src, dst = cur, cur ^ 1
         # one fused pass == Tp steps; level s is needed on the interior extended by (Tp - s) * r planes
         # towards a neighbour (recomputed in the deep halo) and never beyond the global frame
@@ -88,27 +106,32 @@ def _worker(rank, nranks, port, kernel, gst, dtname, nsteps, tfuse, q):
         a = U[src].copy()
         b = a.copy() if Tp > 1 else U[dst].copy()
         for s in range(1, Tp + 1):
-            ext = (Tp - s) * r
+            ext = (Tp - s) * r + more
             zb = H - (0 if first else ext)
             ze = H + nz + (0 if last else ext)
             if info.time_order == 2:
                 assert Tp == 1
             O.step(kernel, shape, (r, r, zb, nx + r, nny - r, ze), coef, b, a, U3)
             a, b = b, a
-        U[dst][H:H + nz] = a[H:H + nz]          # the pass writes the slab's interior planes only
+        # the pass writes the slab's interior planes and the `more` planes towards each neighbour;
+        # only interior points: the x/y frame cells of the destination keep what they held
+        lo, hi = H - (0 if first else more), H + nz + (0 if last else more)
+        U[dst][lo:hi, r:nny - r, r:nx + r] = a[lo:hi, r:nny - r, r:nx + r]
         cur = dst
     q.put((rank, pb.gb[2], nz, U[0][H:H + nz].copy(), U[1][H:H + nz].copy(), cur))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kernel,tfuse,nranks", [(1, 4, 2), (1, 3, 3), (5, 2, 2), (0, 1, 2), (2, 3, 2)])
-def test_deep_halo_schedule_matches_global_oracle(oracle, kernel, tfuse, nranks):
+@pytest.mark.parametrize("kernel,tfuse,nranks,group", [(1, 4, 2, 1), (1, 3, 3, 1), (5, 2, 2, 1), (0, 1, 2, 1), (2, 3, 2, 1),
+                                                       (1, 4, 2, 3), (1, 2, 3, 4), (1, 1, 2, 4), (2, 3, 2, 2)])
+def test_deep_halo_schedule_matches_global_oracle(oracle, kernel, tfuse, nranks, group):
     gst, dt, nsteps = (12, 10, 13 * nranks + 1), "float64", 11
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(rk, nranks, port, kernel, gst, dt, nsteps, tfuse, q)) for rk in range(nranks)]
+    procs = [ctx.Process(target=_worker, args=(rk, nranks, port, kernel, gst, dt, nsteps, tfuse, q, group))
+             for rk in range(nranks)]
     [p.start() for p in procs]
     res = [q.get(timeout=180) for _ in range(nranks)]
     [p.join(timeout=60) for p in procs]
