@@ -163,3 +163,33 @@ def test_exchange_geometry_is_the_reference_z_halo():
     assert G.plan_halo_exchange(16, 4, 0, 2)["send_down"] == -1
     with pytest.raises(G.GirihError):
         G.plan_halo_exchange(3, 4, 0, 2)                      # slab thinner than the halo
+
+
+def test_exchange_schedule_properties():
+    """girih_plan_fused_exchanges: every pass finds the halo planes it reads, no exchange exceeds the cap,
+    group = 1 is the one-exchange-per-pass schedule, and larger groups only remove exchanges."""
+    for nsteps in (0, 1, 2, 7, 33, 130):
+        for T in (1, 2, 3, 4):
+            sizes = G.plan_fused_passes(nsteps, T)
+            for r in (1, 4):
+                base = G.plan_fused_exchanges(nsteps, T, r, T * r, 1)
+                assert base == [s * r for s in sizes]
+                for cap in (T * r, 2 * T * r, 4 * T * r):
+                    prev = len([d for d in base if d])
+                    for group in (1, 2, 3, 4):
+                        d = G.plan_fused_exchanges(nsteps, T, r, cap, group)
+                        assert len(d) == len(sizes)
+                        ready = 0
+                        for s, dep in zip(sizes, d):
+                            assert 0 <= dep <= cap
+                            if dep:
+                                assert ready < s * r          # exchanges happen only when needed
+                                ready = dep
+                            assert ready >= s * r
+                            ready -= s * r
+                        n = len([x for x in d if x])
+                        assert n <= prev
+                        prev = n
+    assert G.plan_fused_exchanges(513, 4, 1, 16, 4)[:5] == [16, 0, 0, 0, 16]
+    with pytest.raises(G.GirihError):
+        G.plan_fused_exchanges(10, 4, 1, 3, 1)                # cap below one pass's depth
