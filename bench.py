@@ -59,6 +59,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
+        # index: one GPU or a comma separated list; with several GPUs the per-GPU medians are reported too
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
@@ -82,20 +83,26 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:   # noqa: BLE001
             self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
+        sm, mx, reasons, pw, per = [], [], set(), [], {}
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
                 sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                per.setdefault(f[0], []).append(float(f[1]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if len(per) > 1:   # multi-GPU run: the slowest GPU sets the pace of a synchronised stepper
+            med = {k: statistics.median(v) for k, v in per.items()}
+            out["sm_mhz_per_gpu"] = [med[k] for k in sorted(med, key=int)]
+            out["sm_mhz"] = min(med.values())
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -242,7 +249,7 @@ def main_ours(args):
     # ---- device-resident timing ----
     for _ in range(args.warmup):
         s.run_fused(nsteps, tf)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local if world == 1 else ",".join(str(i) for i in range(world)))
     if rank == 0:
         sampler.start()
     barrier()
@@ -256,6 +263,12 @@ def main_ours(args):
         launches += s.launch_info()["kernels"]
     barrier()
     wall = time.perf_counter() - t0
+    per_rank_compute = None
+    if world > 1:   # who is waiting for whom: compute time per rank (total - exchange/wait), ms per step
+        mine = torch.tensor([(dev_ms - comm_ms) / args.steps], dtype=torch.float64, device="cuda")
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        per_rank_compute = [float(v.item()) for v in allv]
     comm_ms = allmax(comm_ms)
     clocks = sampler.stop() if rank == 0 else None
     dev_s = allmax(dev_ms * 1e-3)
@@ -362,6 +375,7 @@ def main_ours(args):
                        "timing": "cudaEvents on the launching stream inside the C ABI, max over ranks",
                        "halo_exchange": (None if world == 1 else
                                          {"ms_per_step_max_over_ranks": comm_ms / args.steps,
+                                          "compute_ms_per_step_per_rank": per_rank_compute,
                                           "overlap_with_interior": bool(args.overlap)}),
                        "wall_s": wall},
             "clocks": clocks,
