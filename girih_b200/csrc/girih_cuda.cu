@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "kernels_naive.cuh"
 #include "launch.h"
+#include "layout.h"
 #include "nccl_dyn.h"
 #include "stencil_expr.cuh"
 
@@ -131,7 +132,6 @@ extern "C" int girih_gpu_count(int *n) {
   return GIRIH_OK;
 }
 
-static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 extern "C" int girih_gpu_create(girih_gpu_ctx **out, int device, int target_kernel, int elem_size,
                                 const int st[3], const int ds[3], int rank, int nranks) {
@@ -155,24 +155,10 @@ extern "C" int girih_gpu_create(girih_gpu_ctx **out, int device, int target_kern
   auto bail = [&](int status) { girih_gpu_destroy(c); return status; };
   if (cudaSetDevice(device) != cudaSuccess) return bail(GIRIH_ERR_CUDA);
 
-  // HBM layout (see DevGrid): interior x origin 128-byte aligned, rows padded to 128 bytes plus one
-  // spare 128-byte group so that the last (partial) tile's vector accesses stay inside the row.
-  const int epl = 128 / elem_size;            // elements per 128 bytes
+  // HBM layout (see DevGrid and layout.h)
   const int guard = c->kd.max_tfuse * r;      // deepest halo / overlap any stepper uses
   DevGrid &g = c->g;
-  g.r = r; g.nx = st[0]; g.ny = st[1]; g.nz = st[2];
-  g.X0 = epl;                                 // >= guard, keeps x = X0 line aligned
-  g.Y0 = std::max(guard, r);
-  // z-slab runs keep up to 4 fused passes' worth of halo planes so that one exchange can serve several
-  // passes (run_passes); a single slab needs only the pipeline's own guard planes
-  const int zguard = std::max(guard, r) * (nranks > 1 ? 4 : 1);
-  g.Z0 = zguard;
-  g.px = round_up(g.X0 + g.nx + std::max(guard, r), epl) + epl;
-  g.ny_dev = g.Y0 + g.ny + std::max(guard, r);
-  g.nz_dev = g.Z0 + g.nz + zguard;
-  g.pxy = (long long)g.px * g.ny_dev;
-  g.zlo = (rank == 0) ? g.Z0 : -(1 << 30);
-  g.zhi = (rank == nranks - 1) ? g.Z0 + g.nz : (1 << 30);
+  const int zguard = make_dev_grid(g, st, r, c->kd.max_tfuse, elem_size, rank, nranks);
   c->halo_max = (nranks > 1) ? std::min(zguard, std::max(g.nz, std::max(guard, r))) : zguard;
   c->nz_min = g.nz;
   c->arr_elems = (size_t)g.pxy * g.nz_dev;

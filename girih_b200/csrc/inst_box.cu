@@ -27,7 +27,8 @@ static cudaError_t launch_box_t(const StreamLaunch &s) {
   zchunk = std::min(zchunk, std::max(nz, 1));
   a.zchunk = zchunk;
   dim3 grid((g.nx + WX - 1) / WX, (g.ny + NW - 1) / NW, (nz + zchunk - 1) / zchunk);
-  k_box_march<R, NW, FM><<<grid, 32 * NW, 0, s.stream>>>(a);
+  auto kfn = k_box_march<R, NW, FM>;
+  GIRIH_LAUNCH(kfn, grid, 32 * NW, 0, s.stream, a);
   return cudaGetLastError();
 }
 

@@ -60,7 +60,7 @@ static cudaError_t launch_r1_t(const StreamLaunch &s) {
   a.ze1 = s.ze1;
   const int nch1 = (s.ze1 > s.zb1) ? (s.ze1 - s.zb1 + zchunk - 1) / zchunk : 0;
   dim3 grid(ntx, nty, a.nch0 + nch1);
-  kfn<<<grid, 32 * NW, Cfg::SMEM, s.stream>>>(a);
+  GIRIH_LAUNCH(kfn, grid, 32 * NW, Cfg::SMEM, s.stream, a);
   return cudaGetLastError();
 }
 
@@ -125,7 +125,8 @@ static cudaError_t launch_march_t(const StreamLaunch &s) {
   zchunk = std::min(zchunk, std::max(nz, 1));
   a.zchunk = zchunk;
   dim3 grid((g.nx + WX - 1) / WX, (g.ny + TY - 1) / TY, (nz + zchunk - 1) / zchunk);
-  k_r1_march<K, R, PY, NWY, FM><<<grid, 32 * NWY, 0, s.stream>>>(a);
+  auto kfn = k_r1_march<K, R, PY, NWY, FM>;
+  GIRIH_LAUNCH(kfn, grid, 32 * NWY, 0, s.stream, a);
   return cudaGetLastError();
 }
 

@@ -29,7 +29,7 @@ static cudaError_t launch_r4_t(const StreamLaunch &s) {
   auto kfn = k_r4<K, R, NW>;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
   if (e != cudaSuccess) return e;
-  kfn<<<grid, 32 * NW, Cfg::SMEM, s.stream>>>(a);
+  GIRIH_LAUNCH(kfn, grid, 32 * NW, Cfg::SMEM, s.stream, a);
   return cudaGetLastError();
 }
 
@@ -60,7 +60,7 @@ static cudaError_t launch_r4_strip_t(const StreamLaunch &s) {
   auto kfn = k_r4_strip<K, R, PY, NW, FM>;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
   if (e != cudaSuccess) return e;
-  kfn<<<grid, 32 * NW, Cfg::SMEM, s.stream>>>(a);
+  GIRIH_LAUNCH(kfn, grid, 32 * NW, Cfg::SMEM, s.stream, a);
   return cudaGetLastError();
 }
 
@@ -87,7 +87,7 @@ static cudaError_t launch_r4_async_t(const StreamLaunch &s) {
   auto kfn = k_r4_async<K, R, NW, FM>;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACfg::SMEM);
   if (e != cudaSuccess) return e;
-  kfn<<<grid, 32 * NW, ACfg::SMEM, s.stream>>>(a);
+  GIRIH_LAUNCH(kfn, grid, 32 * NW, ACfg::SMEM, s.stream, a);
   return cudaGetLastError();
 }
 

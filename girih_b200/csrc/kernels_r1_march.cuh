@@ -160,7 +160,7 @@ k_r1_march(const MarchArgs<R> a) {
           n.zm = zm[j][e];
           n.zp = zp[j][e];
           if constexpr (NCA > 0) {
-            RegCoef<R, NCA> rc;
+            RegCoef<R, KTraits<K>::NCA> rc;   // (spelled out: g++ 13 rejects the local constexpr here)
 #pragma unroll
             for (int m = 0; m < NCA; ++m) rc.v[m] = cf[m][e];
             o[e] = StencilExpr<K>::template eval<R, FM>(n, rc, (R)0, (R)0);

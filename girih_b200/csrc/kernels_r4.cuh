@@ -273,6 +273,7 @@ template <typename R, int PH> struct RegNb4A {
 //     __syncthreads -> issue G(z+3) (its buffer was read last in iteration z-1, which every warp has left)
 //     -> compute plane z
 // ------------------------------------------------------------------------------------------------------
+#ifndef GIRIH_CUDA_EMU
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
@@ -281,6 +282,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+#endif   // the test suite's CPU SIMT emulator (tests/cuda_emu) supplies its own queue-based versions
 
 template <typename R, int NW> struct R4ACfg {
   using B = R4Cfg<R, NW>;

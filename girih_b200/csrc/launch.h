@@ -5,6 +5,13 @@
 
 #include "common.cuh"
 
+// Every kernel of the library is started through this one macro.  The CPU SIMT emulator of the test
+// suite (tests/cuda_emu, test infrastructure only) compiles the same kernel and launcher sources with
+// its own definition; the product build always takes the <<<>>> form below.
+#ifndef GIRIH_LAUNCH
+#define GIRIH_LAUNCH(kfn, grid, block, smem, stream, ...) (kfn)<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 namespace girih {
 
 struct StreamLaunch {

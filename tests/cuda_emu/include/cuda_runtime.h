@@ -1,0 +1,179 @@
+// cuda_runtime.h of the CPU SIMT emulator -- TEST INFRASTRUCTURE, never part of the product.
+//
+// The kernel sources under girih_b200/csrc are compiled a second time, unchanged, as plain C++ against
+// this header (g++ -DGIRIH_CUDA_EMU -I tests/cuda_emu/include).  Every CUDA thread of a CTA becomes a
+// user-level fiber; __syncthreads, warp shuffles/votes and cp.async are executed with their CUDA
+// semantics by the small scheduler in emu_runtime.cpp.  This lets `pytest -m "not gpu"` run the real
+// kernel code (tiling, masks, plane rotation, halo handling) against the oracle without a GPU; speed
+// is irrelevant and nothing here is reachable from libgirih_cuda.so.
+#pragma once
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <functional>
+
+#ifndef GIRIH_CUDA_EMU
+#error "this header is only for the emulator build of the test suite"
+#endif
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __launch_bounds__(...)
+#define __shared__ __thread   /* not thread_local: no dynamic-initialisation wrapper for extern declarations */
+#define __align__(n) __attribute__((aligned(n)))
+
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct __attribute__((aligned(16))) double2 { double x, y; };
+struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorLaunchFailure = 719 };
+typedef void *cudaStream_t;
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaDevAttrMultiProcessorCount = 16 };
+
+namespace cuda_emu {
+
+constexpr size_t SMEM_BYTES = 227 * 1024;   // dynamic shared memory a CTA may ask for on sm_100
+
+struct Thread {
+  void *sp;          // saved stack pointer while the fiber is switched out
+  char *stack;
+  uint3 tid;
+  int lin, lane, warp;
+  bool done;
+  unsigned ncoll;    // warp collectives executed so far
+  // cp.async: copies of committed groups that have not been waited for yet
+  struct Copy { void *dst; const void *src; };
+  Copy *q;
+  int qcap, qn;            // copies queued (all groups)
+  int gend[16], ngroups;   // end index of each committed group (FIFO)
+};
+struct Warp {
+  unsigned long long buf[2][32];
+  long arrived[2];
+};
+struct Block {
+  Thread *th;
+  Warp *warps;
+  int nthreads, alive;
+  long bar_gen;
+  int bar_count;
+  uint3 bid;
+  dim3 bdim, gdim;
+  void *main_sp;
+  int cur;
+  long idle;
+  const std::function<void()> *entry;
+};
+extern thread_local Block *B;
+extern thread_local Thread *TH;
+extern int last_error;
+
+void yield();
+void syncthreads();
+unsigned long long warp_exchange(unsigned long long v, int src_lane);   // every lane deposits, reads src_lane
+void launch_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()> &entry);
+void cp_async_issue(void *dst, const void *src);
+void cp_async_commit_group();
+void cp_async_wait_group(int n);
+
+template <typename F, typename... A>
+static inline void launch(F kfn, dim3 grid, dim3 block, size_t smem, cudaStream_t, A... args) {
+  std::function<void()> entry = [=]() { kfn(args...); };
+  launch_impl(grid, block, smem, entry);
+}
+
+template <typename T> static inline unsigned long long to_bits(T v) {
+  static_assert(sizeof(T) <= 8, "shuffle payload");
+  unsigned long long b = 0;
+  memcpy(&b, &v, sizeof(T));
+  return b;
+}
+template <typename T> static inline T from_bits(unsigned long long b) {
+  T v;
+  memcpy(&v, &b, sizeof(T));
+  return v;
+}
+
+}  // namespace cuda_emu
+
+#define GIRIH_LAUNCH(kfn, grid, block, smem, stream, ...) \
+  cuda_emu::launch((kfn), dim3(grid), dim3(block), (size_t)(smem), (stream), __VA_ARGS__)
+
+#define threadIdx (cuda_emu::TH->tid)
+#define blockIdx (cuda_emu::B->bid)
+#define blockDim (cuda_emu::B->bdim)
+#define gridDim (cuda_emu::B->gdim)
+
+static inline void __syncthreads() { cuda_emu::syncthreads(); }
+
+// full-mask warp primitives (the only form the kernels use)
+template <typename T> static inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
+  const int lane = cuda_emu::TH->lane, src = lane - (int)delta;
+  const unsigned long long got = cuda_emu::warp_exchange(cuda_emu::to_bits(v), src < 0 ? lane : src);
+  return cuda_emu::from_bits<T>(got);
+}
+template <typename T> static inline T __shfl_down_sync(unsigned, T v, unsigned delta) {
+  const int lane = cuda_emu::TH->lane, src = lane + (int)delta;
+  const unsigned long long got = cuda_emu::warp_exchange(cuda_emu::to_bits(v), src > 31 ? lane : src);
+  return cuda_emu::from_bits<T>(got);
+}
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src) {
+  return cuda_emu::from_bits<T>(cuda_emu::warp_exchange(cuda_emu::to_bits(v), src & 31));
+}
+unsigned __ballot_sync(unsigned mask, int pred);
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
+static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
+
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+
+// IEEE round-to-nearest arithmetic, never contracted (the emulator is compiled with -ffp-contract=off)
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmaf_rn(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __fma_rn(double a, double b, double c) { return __builtin_fma(a, b, c); }
+
+using std::max;
+using std::min;
+
+// the slice of the runtime API the launchers call
+static inline cudaError_t cudaGetLastError() {
+  const int e = cuda_emu::last_error;
+  cuda_emu::last_error = 0;
+  return e;
+}
+template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, int, int value) {
+  return (size_t)value <= cuda_emu::SMEM_BYTES ? cudaSuccess : cudaErrorInvalidValue;
+}
+static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetAttribute(int *v, int attr, int) {
+  if (attr == cudaDevAttrMultiProcessorCount) *v = 148;
+  return cudaSuccess;
+}
+template <typename F>
+static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *occ, F, int, size_t) {
+  *occ = 1;
+  return cudaSuccess;
+}
+
+// cp.async wrappers of kernels_r4.cuh (the product versions are inline PTX)
+namespace girih {
+static inline void cp_async16(void *smem, const void *gmem) { cuda_emu::cp_async_issue(smem, gmem); }
+static inline void cp_async_commit() { cuda_emu::cp_async_commit_group(); }
+template <int N> static inline void cp_async_wait() { cuda_emu::cp_async_wait_group(N); }
+}  // namespace girih
