@@ -121,8 +121,11 @@ def make_problem(kernel, gstencil, dtype=np.float64, rank=0, nranks=1, alignment
 class GpuStepper:
     """Device state of one z-slab + the time steppers (girih_gpu_ctx)."""
 
+    # the native library behind this class: libgirih_cuda.so (raises when it has not been built)
+    _load = staticmethod(_lib.cuda)
+
     def __init__(self, kernel, stencil, shape, dtype=np.float64, device=0, rank=0, nranks=1):
-        self._lib = _lib.cuda()
+        self._lib = self._load()
         self._ctx = C.c_void_p()
         self.kernel, self.dtype = kernel, np.dtype(dtype)
         self.stencil, self.shape = tuple(stencil), tuple(shape)
@@ -155,10 +158,10 @@ class GpuStepper:
             pass
 
     # -- communicator -------------------------------------------------------------------------
-    @staticmethod
-    def comm_unique_id() -> bytes:
+    @classmethod
+    def comm_unique_id(cls) -> bytes:
         buf = C.create_string_buffer(128)
-        rc = _lib.cuda().girih_gpu_comm_unique_id(buf, 128)
+        rc = cls._load().girih_gpu_comm_unique_id(buf, 128)
         if rc:
             raise GirihError(rc, "girih_gpu_comm_unique_id")
         return buf.raw

@@ -342,14 +342,17 @@ static int fast_copy(girih_gpu_ctx *c, void *dev, void *host, bool to_device) {
   if (rc) return rc;
   const size_t bytes = (size_t)c->hshape[0] * c->hshape[1] * c->hshape[2] * c->es;
   const int grid = 148 * 16;
+  const int hx = c->hshape[0], hy = c->hshape[1], hz = c->hshape[2];
+  auto repitch = [&](auto kd, auto kf) {   // kd / kf: the double / float instantiation of one direction
+    if (c->es == 8) GIRIH_LAUNCH(kd, grid, 256, 0, c->s_comp, c->g, (double *)dev, (double *)c->d_stage, hx, hy, hz);
+    else GIRIH_LAUNCH(kf, grid, 256, 0, c->s_comp, c->g, (float *)dev, (float *)c->d_stage, hx, hy, hz);
+  };
   if (to_device) {
     CU(cudaMemcpyAsync(c->d_stage, host, bytes, cudaMemcpyHostToDevice, c->s_comp));
-    if (c->es == 8) k_repitch<double, true><<<grid, 256, 0, c->s_comp>>>(c->g, (double *)dev, (double *)c->d_stage, c->hshape[0], c->hshape[1], c->hshape[2]);
-    else            k_repitch<float, true><<<grid, 256, 0, c->s_comp>>>(c->g, (float *)dev, (float *)c->d_stage, c->hshape[0], c->hshape[1], c->hshape[2]);
+    repitch(k_repitch<double, true>, k_repitch<float, true>);
     CU(cudaGetLastError());
   } else {
-    if (c->es == 8) k_repitch<double, false><<<grid, 256, 0, c->s_comp>>>(c->g, (double *)dev, (double *)c->d_stage, c->hshape[0], c->hshape[1], c->hshape[2]);
-    else            k_repitch<float, false><<<grid, 256, 0, c->s_comp>>>(c->g, (float *)dev, (float *)c->d_stage, c->hshape[0], c->hshape[1], c->hshape[2]);
+    repitch(k_repitch<double, false>, k_repitch<float, false>);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(host, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->s_comp));
   }
@@ -489,8 +492,9 @@ static cudaError_t launch_naive_t(girih_gpu_ctx *c, int dst, int xb, int yb, int
   dim3 grid((xe - xb + 63) / 64, (ye - yb + 3) / 4, ze - zb);
   R *u = (R *)c->dU[dst];
   const R *v = (const R *)c->dU[dst ^ 1];
-  k_naive<K, R, FM><<<grid, block, 0, c->s_comp>>>(c->g, u, v, (const R *)c->dU3, (const R *)c->dCoef,
-                                              (long long)c->arr_elems, make_cc<R>(c), xb, yb, zb, xe, ye, ze);
+  auto kfn = k_naive<K, R, FM>;
+  GIRIH_LAUNCH(kfn, grid, block, 0, c->s_comp, c->g, u, v, (const R *)c->dU3, (const R *)c->dCoef,
+               (long long)c->arr_elems, make_cc<R>(c), xb, yb, zb, xe, ye, ze);
   c->n_kernels++;
   return cudaGetLastError();
 }
@@ -984,8 +988,13 @@ extern "C" int girih_gpu_scan_u1(girih_gpu_ctx *c, uint64_t *n_nan_inf, uint64_t
   // the reference scans all ln_domain cells including the x padding, which is zero; count the
   // padding cells as zeros to report the same percentage
   const int hx = c->g.nx + 2 * c->g.r;
-  if (c->es == 8) k_scan<double><<<148 * 8, 256, 0, c->s_comp>>>(c->g, (const double *)c->dU[0], hx, c->hshape[1], c->hshape[2], c->d_scan);
-  else            k_scan<float><<<148 * 8, 256, 0, c->s_comp>>>(c->g, (const float *)c->dU[0], hx, c->hshape[1], c->hshape[2], c->d_scan);
+  if (c->es == 8) {
+    auto kfn = k_scan<double>;
+    GIRIH_LAUNCH(kfn, 148 * 8, 256, 0, c->s_comp, c->g, (const double *)c->dU[0], hx, c->hshape[1], c->hshape[2], c->d_scan);
+  } else {
+    auto kfn = k_scan<float>;
+    GIRIH_LAUNCH(kfn, 148 * 8, 256, 0, c->s_comp, c->g, (const float *)c->dU[0], hx, c->hshape[1], c->hshape[2], c->d_scan);
+  }
   CU(cudaGetLastError());
   unsigned long long h[2];
   CU(cudaMemcpyAsync(h, c->d_scan, sizeof(h), cudaMemcpyDeviceToHost, c->s_comp));

@@ -23,6 +23,11 @@ struct NcclDyn {
 static char g_nccl_err[256] = "not attempted";
 static inline const char *nccl_dyn_error() { return g_nccl_err; }
 
+#ifdef GIRIH_CUDA_EMU
+// test suite's CPU emulator build (tests/cuda_emu): ranks are host threads, NCCL is an in-process mailbox
+NcclDyn *emu_nccl_table();
+static inline NcclDyn *nccl_dyn() { return emu_nccl_table(); }
+#else
 static inline NcclDyn *nccl_dyn() {
   static NcclDyn tab;
   static int state = 0;   // 0 = not tried, 1 = ok, -1 = failed
@@ -56,3 +61,4 @@ static inline NcclDyn *nccl_dyn() {
   }
   return state == 1 ? &tab : nullptr;
 }
+#endif

@@ -38,36 +38,40 @@ def cuda() -> C.CDLL:
         if not os.path.exists(CUDA_LIB):
             raise ImportError(f"{CUDA_LIB} is missing: build it with `make` (nvcc, sm_100a). "
                               "There is no Python or CPU fallback.")
-        lib = C.CDLL(CUDA_LIB, mode=C.RTLD_GLOBAL)
-        P, I = C.c_void_p, C.c_int
-        lib.girih_kernel_info.argtypes = [I, C.POINTER(KernelDescC)]
-        lib.girih_gpu_count.argtypes = [C.POINTER(I)]
-        lib.girih_gpu_create.argtypes = [C.POINTER(P), I, I, I, C.POINTER(I), C.POINTER(I), I, I]
-        lib.girih_gpu_destroy.argtypes = [P]
-        lib.girih_gpu_destroy.restype = None
-        lib.girih_gpu_comm_unique_id.argtypes = [P, C.c_size_t]
-        lib.girih_gpu_comm_init.argtypes = [P, P, C.c_size_t]
-        lib.girih_gpu_upload.argtypes = [P, P, P, P, P]
-        lib.girih_gpu_download.argtypes = [P, P, P]
-        lib.girih_gpu_upload_fields.argtypes = [P, P, P]
-        lib.girih_gpu_run_single.argtypes = [P, I, I]
-        lib.girih_gpu_run_fused.argtypes = [P, I, I]
-        lib.girih_gpu_step_box.argtypes = [P, I, I, I, I, I, I, I]
-        lib.girih_gpu_time_pass.argtypes = [P, I, I, C.POINTER(C.c_double)]
-        lib.girih_gpu_last_elapsed_ms.argtypes = [P] + [C.POINTER(C.c_double)] * 3
-        lib.girih_gpu_last_launch_info.argtypes = [P] + [C.POINTER(I)] * 4
-        lib.girih_gpu_scan_u1.argtypes = [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
-        lib.girih_gpu_set_option.argtypes = [P, C.c_char_p, I]
-        lib.girih_gpu_autotune.argtypes = [P, I, I, C.POINTER(I), C.POINTER(I), C.POINTER(C.c_double)]
-        lib.girih_plan_fused_passes.argtypes = [I, I, C.POINTER(I), I, C.POINTER(I)]
-        lib.girih_plan_fused_exchanges.argtypes = [I, I, I, I, I, C.POINTER(I), I, C.POINTER(I)]
-        lib.girih_plan_halo_exchange.argtypes = [I, I, I, I] + [C.POINTER(I)] * 4
-        lib.girih_gpu_strerror.argtypes = [I]
-        lib.girih_gpu_strerror.restype = C.c_char_p
-        lib.girih_gpu_last_error.argtypes = [P]
-        lib.girih_gpu_last_error.restype = C.c_char_p
-        _cuda = lib
+        _cuda = declare(C.CDLL(CUDA_LIB, mode=C.RTLD_GLOBAL))
     return _cuda
+
+
+def declare(lib: C.CDLL) -> C.CDLL:
+    """ctypes prototypes of every entry point of include/girih_cuda.h on a loaded library."""
+    P, I = C.c_void_p, C.c_int
+    lib.girih_kernel_info.argtypes = [I, C.POINTER(KernelDescC)]
+    lib.girih_gpu_count.argtypes = [C.POINTER(I)]
+    lib.girih_gpu_create.argtypes = [C.POINTER(P), I, I, I, C.POINTER(I), C.POINTER(I), I, I]
+    lib.girih_gpu_destroy.argtypes = [P]
+    lib.girih_gpu_destroy.restype = None
+    lib.girih_gpu_comm_unique_id.argtypes = [P, C.c_size_t]
+    lib.girih_gpu_comm_init.argtypes = [P, P, C.c_size_t]
+    lib.girih_gpu_upload.argtypes = [P, P, P, P, P]
+    lib.girih_gpu_download.argtypes = [P, P, P]
+    lib.girih_gpu_upload_fields.argtypes = [P, P, P]
+    lib.girih_gpu_run_single.argtypes = [P, I, I]
+    lib.girih_gpu_run_fused.argtypes = [P, I, I]
+    lib.girih_gpu_step_box.argtypes = [P, I, I, I, I, I, I, I]
+    lib.girih_gpu_time_pass.argtypes = [P, I, I, C.POINTER(C.c_double)]
+    lib.girih_gpu_last_elapsed_ms.argtypes = [P] + [C.POINTER(C.c_double)] * 3
+    lib.girih_gpu_last_launch_info.argtypes = [P] + [C.POINTER(I)] * 4
+    lib.girih_gpu_scan_u1.argtypes = [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.girih_gpu_set_option.argtypes = [P, C.c_char_p, I]
+    lib.girih_gpu_autotune.argtypes = [P, I, I, C.POINTER(I), C.POINTER(I), C.POINTER(C.c_double)]
+    lib.girih_plan_fused_passes.argtypes = [I, I, C.POINTER(I), I, C.POINTER(I)]
+    lib.girih_plan_fused_exchanges.argtypes = [I, I, I, I, I, C.POINTER(I), I, C.POINTER(I)]
+    lib.girih_plan_halo_exchange.argtypes = [I, I, I, I] + [C.POINTER(I)] * 4
+    lib.girih_gpu_strerror.argtypes = [I]
+    lib.girih_gpu_strerror.restype = C.c_char_p
+    lib.girih_gpu_last_error.argtypes = [P]
+    lib.girih_gpu_last_error.restype = C.c_char_p
+    return lib
 
 
 def host(elem_size: int) -> C.CDLL:

@@ -21,7 +21,7 @@ namespace cuda_emu {
 
 thread_local Block *B = nullptr;
 thread_local Thread *TH = nullptr;
-int last_error = 0;
+__thread int last_error = 0;
 static int g_sched = 0;
 static constexpr size_t STACK_BYTES = 256 * 1024;
 

@@ -78,7 +78,7 @@ struct Block {
 };
 extern thread_local Block *B;
 extern thread_local Thread *TH;
-extern int last_error;
+extern __thread int last_error;
 
 void yield();
 void syncthreads();
@@ -169,6 +169,54 @@ template <typename F>
 static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *occ, F, int, size_t) {
   *occ = 1;
   return cudaSuccess;
+}
+
+// ---- the rest of the runtime API girih_cuda.cu uses: device memory is host memory, every stream
+// ---- operation completes before the call returns (program order per rank), events carry wall-clock stamps
+typedef struct cuda_emu_event *cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2,
+                      cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+struct cudaPitchedPtr { void *ptr; size_t pitch, xsize, ysize; };
+struct cudaPos { size_t x, y, z; };
+struct cudaExtent { size_t width, height, depth; };
+struct cudaMemcpy3DParms {
+  void *srcArray; cudaPos srcPos; cudaPitchedPtr srcPtr;
+  void *dstArray; cudaPos dstPos; cudaPitchedPtr dstPtr;
+  cudaExtent extent; cudaMemcpyKind kind;
+};
+static inline cudaPitchedPtr make_cudaPitchedPtr(void *d, size_t p, size_t xsz, size_t ysz) { return cudaPitchedPtr{d, p, xsz, ysz}; }
+static inline cudaPos make_cudaPos(size_t x, size_t y, size_t z) { return cudaPos{x, y, z}; }
+static inline cudaExtent make_cudaExtent(size_t w, size_t h, size_t d) { return cudaExtent{w, h, d}; }
+
+cudaError_t cudaGetDeviceCount(int *n);          // CUDA_EMU_DEVICES (default 8)
+cudaError_t cudaSetDevice(int d);
+cudaError_t cudaMalloc(void **p, size_t bytes);  // 256-byte aligned like the real allocator, poisoned
+template <typename T> static inline cudaError_t cudaMalloc(T **p, size_t bytes) { return cudaMalloc((void **)p, bytes); }
+cudaError_t cudaFree(void *p);
+cudaError_t cudaMemset(void *p, int v, size_t bytes);
+cudaError_t cudaMemcpy(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind);
+cudaError_t cudaMemcpy3D(const cudaMemcpy3DParms *p);
+static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t bytes, cudaStream_t) { return cudaMemset(p, v, bytes); }
+static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind k, cudaStream_t) { return cudaMemcpy(d, s, n, k); }
+static inline cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms *p, cudaStream_t) { return cudaMemcpy3D(p); }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned flags);
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned flags, int prio);
+cudaError_t cudaStreamDestroy(cudaStream_t s);
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = -5; return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t *e);
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t e);
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s);
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
+const char *cudaGetErrorString(cudaError_t e);
+
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
+  return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
 
 // cp.async wrappers of kernels_r4.cuh (the product versions are inline PTX)
