@@ -74,6 +74,8 @@ class HostProblem:
     rank: int
     nranks: int
     r: int
+    dims: tuple          # process topology (npx, npy, npz); z-slabs: (1, 1, nranks)
+    coords: tuple        # this rank's position in it
     U1: np.ndarray       # [nnz, nny, nnx]
     U2: np.ndarray
     U3: np.ndarray | None
@@ -87,17 +89,21 @@ class HostProblem:
 
 
 def make_problem(kernel, gstencil, dtype=np.float64, rank=0, nranks=1, alignment=8, padding=True,
-                 pinned=False) -> HostProblem:
-    """Host arrays of z-slab `rank`: the C host's init() + init_coeff() + domain_data_fill()."""
+                 pinned=False, topology=None) -> HostProblem:
+    """Host arrays of sub-domain `rank`: the C host's init() + init_coeff() + domain_data_fill().
+    topology = (npx, npy, npz) as --npx/--npy/--npz; default: z-slabs, (1, 1, nranks)."""
     dtype = np.dtype(dtype)
     es = dtype.itemsize
     h = _lib.host(es)
     info = kernel_info(kernel)
-    ls, ds, gb = (C.c_int * 3)(), (C.c_int * 3)(), (C.c_int * 3)()
-    h.girih_host_shapes(kernel, _i3(gstencil), rank, nranks, alignment, int(padding), ls, ds, gb)
+    dims = (1, 1, nranks) if topology is None else tuple(int(d) for d in topology)
+    if dims[0] * dims[1] * dims[2] != nranks:
+        raise ValueError("topology does not match nranks")
+    ls, ds, gb, co = (C.c_int * 3)(), (C.c_int * 3)(), (C.c_int * 3)(), (C.c_int * 3)()
+    h.girih_host_shapes_topo(kernel, _i3(gstencil), rank, _i3(dims), alignment, int(padding), ls, ds, gb, co)
     shape = tuple(ds)
     zyx = (shape[2], shape[1], shape[0])
-    ncoef = int(h.girih_host_coef_size(kernel, _i3(gstencil), rank, nranks, alignment, int(padding)))
+    ncoef = int(h.girih_host_coef_size_topo(kernel, _i3(gstencil), rank, _i3(dims), alignment, int(padding)))
 
     def alloc(sh):
         if pinned:
@@ -109,13 +115,13 @@ def make_problem(kernel, gstencil, dtype=np.float64, rank=0, nranks=1, alignment
     U1, U2 = alloc(zyx), alloc(zyx)
     U3 = alloc(zyx) if info.time_order == 2 else None
     coef = np.zeros(ncoef, dtype)
-    rc = h.girih_host_fill(kernel, _i3(gstencil), rank, nranks, alignment, int(padding),
-                           U1.ctypes.data, U2.ctypes.data, U3.ctypes.data if U3 is not None else None,
-                           coef.ctypes.data)
+    rc = h.girih_host_fill_topo(kernel, _i3(gstencil), rank, _i3(dims), alignment, int(padding),
+                                U1.ctypes.data, U2.ctypes.data, U3.ctypes.data if U3 is not None else None,
+                                coef.ctypes.data)
     if rc:
         raise RuntimeError("girih_host_fill failed")
     return HostProblem(kernel, dtype, tuple(gstencil), tuple(ls), shape, tuple(gb), rank, nranks, info.r,
-                       U1, U2, U3, coef)
+                       dims, tuple(co), U1, U2, U3, coef)
 
 
 class GpuStepper:
@@ -165,6 +171,10 @@ class GpuStepper:
         if rc:
             raise GirihError(rc, "girih_gpu_comm_unique_id")
         return buf.raw
+
+    def set_topology(self, dims, coords):
+        """(npx, npy, npz) and this rank's position; before comm_init.  Default: z-slabs."""
+        self._check(self._lib.girih_gpu_set_topology(self._ctx, _i3(dims), _i3(coords)), "girih_gpu_set_topology")
 
     def comm_init(self, uid: bytes):
         self._check(self._lib.girih_gpu_comm_init(self._ctx, uid, len(uid)), "girih_gpu_comm_init")

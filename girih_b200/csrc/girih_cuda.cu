@@ -68,6 +68,11 @@ struct EvPair { cudaEvent_t a, b; };
 
 struct girih_gpu_ctx {
   int device = 0, kernel = 0, es = 8, rank = 0, nranks = 1;
+  // process topology (src/mpi_utils.c:63-81): dims = (npx, npy, npz), MPI_Cart_create's row-major rank order
+  // (z fastest).  Default: z-slabs only.  Set by girih_gpu_set_topology.
+  int dims[3] = {1, 1, 1}, coords[3] = {0, 0, 0};
+  void *d_pack = nullptr;             // x/y face staging: [send-, send+, recv-, recv+] x pack_elems
+  size_t pack_elems = 0;
   int hshape[3] = {0, 0, 0};   // host array shape
   int st[3] = {0, 0, 0};       // local interior
   girih_kernel_desc kd{};
@@ -124,6 +129,16 @@ static int fail(girih_gpu_ctx *c, int status, const char *fmt, ...) {
 
 extern "C" const char *girih_gpu_last_error(girih_gpu_ctx *c) { return c ? c->err : ""; }
 
+// rank of the neighbour one step along dimension d (dir = -1 / +1), or -1 at the domain boundary
+// (the non-periodic MPI_Cart_shift of src/mpi_utils.c:78-80)
+static int neighbour(const girih_gpu_ctx *c, int d, int dir) {
+  int q[3] = {c->coords[0], c->coords[1], c->coords[2]};
+  q[d] += dir;
+  if (q[d] < 0 || q[d] >= c->dims[d]) return -1;
+  return (q[0] * c->dims[1] + q[1]) * c->dims[2] + q[2];
+}
+static bool xy_decomposed(const girih_gpu_ctx *c) { return c->dims[0] > 1 || c->dims[1] > 1; }
+
 extern "C" int girih_gpu_count(int *n) {
   int k = 0;
   cudaError_t e = cudaGetDeviceCount(&k);
@@ -150,6 +165,7 @@ extern "C" int girih_gpu_create(girih_gpu_ctx **out, int device, int target_kern
 
   girih_gpu_ctx *c = new girih_gpu_ctx();
   c->device = device; c->kernel = target_kernel; c->es = elem_size; c->rank = rank; c->nranks = nranks;
+  c->dims[2] = nranks; c->coords[2] = rank;
   c->kd = KERNELS[target_kernel];
   for (int d = 0; d < 3; ++d) { c->hshape[d] = ds[d]; c->st[d] = st[d]; }
   auto bail = [&](int status) { girih_gpu_destroy(c); return status; };
@@ -212,6 +228,7 @@ extern "C" void girih_gpu_destroy(girih_gpu_ctx *c) {
   if (c->dCoef) cudaFree(c->dCoef);
   if (c->d_scan) cudaFree(c->d_scan);
   if (c->d_stage) cudaFree(c->d_stage);
+  if (c->d_pack) cudaFree(c->d_pack);
   for (auto &p : c->comm_ev) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
@@ -220,6 +237,25 @@ extern "C" void girih_gpu_destroy(girih_gpu_ctx *c) {
   if (c->s_comp) cudaStreamDestroy(c->s_comp);
   if (c->s_comm) cudaStreamDestroy(c->s_comm);
   delete c;
+}
+
+// Process topology of the run (the reference's --npx/--npy/--npz, src/mpi_utils.c:63-81).  Without this call the
+// ranks form z-slabs.  With npx or npy > 1 the single-step steppers exchange r-deep x and y faces as well
+// (src/mpi_utils.c:116-170) and temporal fusion is not offered, like the reference, whose diamond stepper
+// does not decompose x either (src/kernels/diamond_utils.c:1035-1040).
+extern "C" int girih_gpu_set_topology(girih_gpu_ctx *c, const int dims[3], const int coords[3]) {
+  if (!c || !dims || !coords) return GIRIH_ERR_ARG;
+  if (c->comm) return fail(c, GIRIH_ERR_STATE, "set_topology after comm_init");
+  for (int d = 0; d < 3; ++d)
+    if (dims[d] < 1 || coords[d] < 0 || coords[d] >= dims[d]) return fail(c, GIRIH_ERR_ARG, "bad topology");
+  if (dims[0] * dims[1] * dims[2] != c->nranks) return fail(c, GIRIH_ERR_ARG, "topology does not match the rank count");
+  if ((coords[0] * dims[1] + coords[1]) * dims[2] + coords[2] != c->rank)
+    return fail(c, GIRIH_ERR_ARG, "coordinates do not match the rank (row-major, z fastest)");
+  for (int d = 0; d < 3; ++d) { c->dims[d] = dims[d]; c->coords[d] = coords[d]; }
+  DevGrid &g = c->g;
+  g.zlo = (coords[2] == 0) ? g.Z0 : -(1 << 30);
+  g.zhi = (coords[2] == dims[2] - 1) ? g.Z0 + g.nz : (1 << 30);
+  return GIRIH_OK;
 }
 
 extern "C" int girih_gpu_set_option(girih_gpu_ctx *c, const char *key, int value) {
@@ -262,7 +298,7 @@ static bool frames_match(const girih_gpu_ctx *c, const R *a, const R *b) {
   // (not the halo planes between slabs, which are interior points of the global domain)
   const int nnx = c->hshape[0], nny = c->hshape[1], nnz = c->hshape[2], r = c->g.r;
   const int nx = c->st[0];
-  const bool zfirst = c->rank == 0, zlast = c->rank == c->nranks - 1;
+  const bool zfirst = c->coords[2] == 0, zlast = c->coords[2] == c->dims[2] - 1;
   for (int k = 0; k < nnz; ++k) {
     const bool kframe = (zfirst && k < r) || (zlast && k >= nnz - r);
     for (int j = 0; j < nny; ++j) {
@@ -420,26 +456,103 @@ extern "C" int girih_plan_halo_exchange(int nz, int depth, int rank, int nranks,
 // src/mpi_utils.c:173-200 generalised from r to depth = T*r planes).  Planes are contiguous,
 // so no pack/unpack kernel is needed.
 static int exchange_z(girih_gpu_ctx *c, void *arr, int depth, cudaStream_t s) {
-  if (c->nranks == 1) return GIRIH_OK;
+  if (c->dims[2] == 1) return GIRIH_OK;
   if (!c->comm) return fail(c, GIRIH_ERR_STATE, "girih_gpu_comm_init was not called");
   const DevGrid &g = c->g;
   const size_t plane_b = (size_t)g.pxy * c->es;
   const size_t count = (size_t)depth * plane_b;
   char *base = (char *)arr;
-  const int up = c->rank + 1, dn = c->rank - 1;
+  const int up = neighbour(c, 2, +1), dn = neighbour(c, 2, -1);
   int sd, rd, su, ru;
-  if (girih_plan_halo_exchange(g.nz, depth, c->rank, c->nranks, &sd, &rd, &su, &ru) != GIRIH_OK)
+  if (girih_plan_halo_exchange(g.nz, depth, c->coords[2], c->dims[2], &sd, &rd, &su, &ru) != GIRIH_OK)
     return fail(c, GIRIH_ERR_ARG, "halo depth %d does not fit a slab of %d planes", depth, g.nz);
   NC(nccl_dyn()->GroupStart());
   if (dn >= 0) {
     NC(nccl_dyn()->Send(base + (size_t)(g.Z0 + sd) * plane_b, count, ncclChar, dn, c->comm, s));
     NC(nccl_dyn()->Recv(base + (size_t)(g.Z0 + rd) * plane_b, count, ncclChar, dn, c->comm, s));
   }
-  if (up < c->nranks) {
+  if (up >= 0) {
     NC(nccl_dyn()->Send(base + (size_t)(g.Z0 + su) * plane_b, count, ncclChar, up, c->comm, s));
     NC(nccl_dyn()->Recv(base + (size_t)(g.Z0 + ru) * plane_b, count, ncclChar, up, c->comm, s));
   }
   NC(nccl_dyn()->GroupEnd());
+  return GIRIH_OK;
+}
+
+// ---- x / y faces (src/mpi_utils.c:116-170; the reference's sub_array_copy pack/unpack, :31-45) ----------------
+// Copies the box [x0, x0+ex) x [y0, y0+ey) x [z0, z0+ez) (device coordinates) of `arr` into / out of a dense buffer.
+template <typename R, bool PACK>
+__global__ void k_face(DevGrid g, R *__restrict__ arr, R *__restrict__ buf, int x0, int y0, int z0, int ex, int ey, int ez) {
+  const long long n = (long long)ex * ey * ez;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % ex);
+    const long long t = i / ex;
+    const int y = (int)(t % ey), z = (int)(t / ey);
+    R *p = arr + ((long long)(z0 + z) * g.ny_dev + (y0 + y)) * g.px + (x0 + x);
+    if (PACK) buf[i] = *p;
+    else *p = buf[i];
+  }
+}
+
+template <bool PACK>
+static cudaError_t launch_face(girih_gpu_ctx *c, void *arr, void *buf, int x0, int y0, int z0, int ex, int ey, int ez,
+                               cudaStream_t s) {
+  const long long n = (long long)ex * ey * ez;
+  const int grid = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  if (c->es == 8) {
+    auto kfn = k_face<double, PACK>;
+    GIRIH_LAUNCH(kfn, grid, 256, 0, s, c->g, (double *)arr, (double *)buf, x0, y0, z0, ex, ey, ez);
+  } else {
+    auto kfn = k_face<float, PACK>;
+    GIRIH_LAUNCH(kfn, grid, 256, 0, s, c->g, (float *)arr, (float *)buf, x0, y0, z0, ex, ey, ez);
+  }
+  c->n_kernels++;
+  return cudaGetLastError();
+}
+
+// r-deep faces of `arr` with the x neighbours, then with the y neighbours.  The y faces span the x halos just
+// received and the z planes exchanged afterwards span both, so edge and corner cells arrive too (the box
+// operator reads them; the star operators do not).
+static int exchange_xy(girih_gpu_ctx *c, void *arr, cudaStream_t s) {
+  if (!xy_decomposed(c)) return GIRIH_OK;
+  if (!c->comm) return fail(c, GIRIH_ERR_STATE, "girih_gpu_comm_init was not called");
+  const DevGrid &g = c->g;
+  const int r = g.r;
+  const size_t xface = (size_t)r * g.ny * g.nz, yface = (size_t)(g.nx + 2 * r) * r * g.nz;
+  const size_t need = std::max(xface, yface);
+  if (c->pack_elems < need) {
+    if (c->d_pack) CU(cudaFree(c->d_pack));
+    c->d_pack = nullptr;
+    CU(cudaMalloc(&c->d_pack, 4 * need * c->es));
+    c->pack_elems = need;
+  }
+  char *buf = (char *)c->d_pack;
+  const size_t slot = c->pack_elems * c->es;   // [0] send-, [1] send+, [2] recv-, [3] recv+
+  for (int d = 0; d < 2; ++d) {
+    if (c->dims[d] == 1) continue;
+    const int lo = neighbour(c, d, -1), hi = neighbour(c, d, +1);
+    // extent of one face and the device coordinates of: my lowest / highest interior layers, the halo layers
+    const int ex = d == 0 ? r : g.nx + 2 * r, ey = d == 0 ? g.ny : r, ez = g.nz;
+    const int xs = d == 0 ? g.X0 : g.X0 - r, ys = g.Y0;
+    const int send_lo[2] = {xs, ys}, send_hi[2] = {d == 0 ? g.X0 + g.nx - r : xs, d == 1 ? g.Y0 + g.ny - r : ys};
+    const int recv_lo[2] = {d == 0 ? g.X0 - r : xs, d == 1 ? g.Y0 - r : ys};
+    const int recv_hi[2] = {d == 0 ? g.X0 + g.nx : xs, d == 1 ? g.Y0 + g.ny : ys};
+    const size_t bytes = (size_t)ex * ey * ez * c->es;
+    if (lo >= 0) CU(launch_face<true>(c, arr, buf + 0 * slot, send_lo[0], send_lo[1], g.Z0, ex, ey, ez, s));
+    if (hi >= 0) CU(launch_face<true>(c, arr, buf + 1 * slot, send_hi[0], send_hi[1], g.Z0, ex, ey, ez, s));
+    NC(nccl_dyn()->GroupStart());
+    if (lo >= 0) {
+      NC(nccl_dyn()->Send(buf + 0 * slot, bytes, ncclChar, lo, c->comm, s));
+      NC(nccl_dyn()->Recv(buf + 2 * slot, bytes, ncclChar, lo, c->comm, s));
+    }
+    if (hi >= 0) {
+      NC(nccl_dyn()->Send(buf + 1 * slot, bytes, ncclChar, hi, c->comm, s));
+      NC(nccl_dyn()->Recv(buf + 3 * slot, bytes, ncclChar, hi, c->comm, s));
+    }
+    NC(nccl_dyn()->GroupEnd());
+    if (lo >= 0) CU(launch_face<false>(c, arr, buf + 2 * slot, recv_lo[0], recv_lo[1], g.Z0, ex, ey, ez, s));
+    if (hi >= 0) CU(launch_face<false>(c, arr, buf + 3 * slot, recv_hi[0], recv_hi[1], g.Z0, ex, ey, ez, s));
+  }
   return GIRIH_OK;
 }
 
@@ -457,8 +570,9 @@ static int timed_exchange(girih_gpu_ctx *c, void *arr, int depth) {
   CU(cudaEventRecord(c->ev_x, c->s_comp));
   CU(cudaStreamWaitEvent(c->s_comm, c->ev_x, 0));
   CU(cudaEventRecord(p.a, c->s_comm));
-  int rc = exchange_z(c, arr, depth, c->s_comm);
+  int rc = exchange_xy(c, arr, c->s_comm);
   if (rc) return rc;
+  if ((rc = exchange_z(c, arr, depth, c->s_comm))) return rc;
   CU(cudaEventRecord(p.b, c->s_comm));
   CU(cudaStreamWaitEvent(c->s_comp, p.b, 0));
   return GIRIH_OK;
@@ -646,7 +760,7 @@ extern "C" int girih_plan_fused_exchanges(int nsteps, int tfuse, int r, int halo
 // passes served by one exchange: the option, else up to 4 while the recomputed planes stay a small
 // fraction of the thinnest slab
 static int halo_group(const girih_gpu_ctx *c, int T, bool overlap) {
-  if (c->nranks == 1 || overlap || c->kd.time_order != 1) return 1;
+  if (c->nranks == 1 || overlap || c->kd.time_order != 1 || xy_decomposed(c)) return 1;
   if (c->opt_halo_group > 0) return c->opt_halo_group;
   int k = 1;
   while (k < 4 && (k + 1) * T * c->g.r <= c->halo_max && k * T * c->g.r * 16 <= c->nz_min) ++k;
@@ -661,6 +775,7 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
   int rc;
   int Tmax = 1;
   for (int s : sizes) Tmax = std::max(Tmax, s);
+  if (xy_decomposed(c)) overlap = false;   // x/y faces are exchanged between whole steps only
   const int group = halo_group(c, Tmax, overlap);
   std::vector<int> depth;
   plan_exchanges(sizes, r, c->halo_max, group, depth);
@@ -680,7 +795,7 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
       }
       // planes beyond the slab that later passes of this group read: computed here, towards neighbours only
       const int ext = ready - T * r;
-      const int lo = (c->rank > 0) ? ext : 0, hi = (c->rank + 1 < c->nranks) ? ext : 0;
+      const int lo = (neighbour(c, 2, -1) >= 0) ? ext : 0, hi = (neighbour(c, 2, +1) >= 0) ? ext : 0;
       CU(launch_pass(c, T, src, dst, zb - lo, ze + hi));
       ready = ext;
       cur = dst;
@@ -801,7 +916,7 @@ extern "C" int girih_gpu_run_fused(girih_gpu_ctx *c, int nsteps, int tfuse) {
   int T = tfuse;
   if (T <= 0) T = c->tuned_tfuse > 0 ? c->tuned_tfuse : default_tfuse(c);
   T = std::min(T, c->kd.max_tfuse);
-  if (c->opt_variant == 1 || c->kernel == 7) T = 1;
+  if (c->opt_variant == 1 || c->kernel == 7 || xy_decomposed(c)) T = 1;
   if (c->nranks > 1) T = std::min(T, std::max(1, c->g.nz / std::max(1, c->g.r)));
   if (T > 1 && !c->frames_equal) return fail(c, GIRIH_ERR_FRAME, "%s", girih_gpu_strerror(GIRIH_ERR_FRAME));
   int rc;

@@ -68,6 +68,12 @@ static cudaError_t launch_r1_t(const StreamLaunch &s) {
 template <int K, typename R, int T>
 static cudaError_t launch_r1_tile(const StreamLaunch &s) {
   if (s.contract) {   // contracted arithmetic: the default tile of each (operator, precision) only
+    if constexpr (K == 1) {
+      if (s.tile == 5408) return launch_r1_t<K, R, T, 4, 8, R1_FM | R1_SPLIT>(s);
+      if (s.tile == 5216) return launch_r1_t<K, R, T, 2, 16, R1_FM | R1_SPLIT>(s);
+      if (s.tile == 7408) return launch_r1_t<K, R, T, 4, 8, R1_FM | R1_REV>(s);
+      if (s.tile == 7216) return launch_r1_t<K, R, T, 2, 16, R1_FM | R1_REV>(s);
+    }
     if constexpr (KTraits<K>::NCA == 0 && sizeof(R) == 8) return launch_r1_t<K, R, T, 4, 8, R1_FM>(s);
     else return launch_r1_t<K, R, T, 2, 16, R1_FM>(s);
   }
@@ -89,6 +95,12 @@ static cudaError_t launch_r1_tile(const StreamLaunch &s) {
   }
 #endif
   if constexpr (K == 1) {
+    // split-barrier variants: 5000 + tile
+    if (s.tile == 5408) return launch_r1_t<K, R, T, 4, 8, R1_SPLIT>(s);
+    if (s.tile == 5216) return launch_r1_t<K, R, T, 2, 16, R1_SPLIT>(s);
+    // decoupled levels (kernels_r1.cuh, REV): 7000 + tile
+    if (s.tile == 7408) return launch_r1_t<K, R, T, 4, 8, R1_REV>(s);
+    if (s.tile == 7216) return launch_r1_t<K, R, T, 2, 16, R1_REV>(s);
     if (s.tile == 312) return launch_r1_t<K, R, T, 3, 12>(s);
     if (s.tile == 310) return launch_r1_t<K, R, T, 3, 10>(s);
     if (s.tile == 316) return launch_r1_t<K, R, T, 3, 16>(s);

@@ -49,7 +49,8 @@ template <typename R, int T, int PY, int NW> struct R1Cfg {
   static constexpr int UY = H - 2 * T;                  // core rows per tile
   static constexpr int PF = (T == 1) ? 2 : 1;           // planes prefetched ahead
   static constexpr int MINB = (T == 1 && NW <= 8) ? 2 : 1;   // resident CTAs per SM aimed for
-  static constexpr size_t SMEM = (size_t)T * 2 * NW * 2 * WX * sizeof(R);
+  static constexpr size_t EDGE_BYTES = (size_t)T * 2 * NW * 2 * WX * sizeof(R);
+  static constexpr size_t SMEM = EDGE_BYTES + 16;   // + the mbarrier of the split-barrier variant
   static_assert(UY > 0 && UX > 0, "tile too small for this fusion depth");
 };
 
@@ -68,6 +69,29 @@ template <typename R> struct RegNb1 {
 };
 
 constexpr int R1_FM = 32;   // DBG flag bit: evaluate with the reference's gcc -mfma contraction
+constexpr int R1_SPLIT = 64;   // DBG flag bit: split (arrive ... wait) CTA barrier instead of __syncthreads
+constexpr int R1_REV = 128;    // DBG flag bit: decoupled levels (T > 1), see the comment in k_r1
+
+// Split CTA barrier on an mbarrier in shared memory: a warp ARRIVES as soon as it has published its edge rows
+// and read its neighbours' (before the arithmetic of the last fused level and the global stores) and WAITS at
+// the top of the next iteration, so the warps of a CTA may drift apart by that much instead of meeting at one
+// point per iteration.  arrive = release, wait = acquire (CTA scope).
+#ifndef GIRIH_CUDA_EMU
+__device__ __forceinline__ void sb_init(unsigned long long *bar, int count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sb_arrive(unsigned long long *bar) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared.b64 st, [%0];\n}\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void sb_wait(unsigned long long *bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n.reg .pred p;\nSB_WAIT:\nmbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n@p bra SB_DONE;\n"
+      "bra SB_WAIT;\nSB_DONE:\n}\n" ::"r"(a), "r"(parity) : "memory");
+}
+#endif   // the test suite's CPU SIMT emulator (tests/cuda_emu) supplies its own versions
 
 template <int PH> struct Phase { static constexpr int value = PH; };
 template <int I> struct Level { static constexpr int value = I; };
@@ -76,6 +100,12 @@ template <int I, int N, typename F> __device__ __forceinline__ void static_for(F
   if constexpr (I < N) {
     f(Level<I>{});
     static_for<I + 1, N>(f);
+  }
+}
+template <int N, typename F> __device__ __forceinline__ void static_for_rev(F &&f) {   // N-1, ..., 0
+  if constexpr (N > 0) {
+    f(Level<N - 1>{});
+    static_for_rev<N - 1>(f);
   }
 }
 
@@ -87,6 +117,16 @@ k_r1(const R1Args<R> a) {
   constexpr int PF = Cfg::PF;
   constexpr int NCA = KTraits<K>::NCA;
   constexpr bool FM = (DBG & R1_FM) != 0;   // contracted (FMA) arithmetic, see stencil_expr.cuh
+  constexpr bool SPLIT = (DBG & R1_SPLIT) != 0;
+  // Decoupled levels (REV): level l+1 lags level l by TWO planes instead of one and the levels of an iteration
+  // run from the deepest to the shallowest.  Level l+1 then consumes what level l produced in the PREVIOUS
+  // iteration, so the T updates of one iteration do not depend on each other (the scheduler may interleave
+  // them freely), the plane a level produces goes into the register plane its consumer has just released
+  // (no extra registers), and the level-0 plane loaded at the end of one iteration is first touched at the
+  // end of the next one.  Price: T-1 more pipeline-fill iterations per z chunk.
+  constexpr bool REV = (DBG & R1_REV) != 0 && T > 1;
+  constexpr int LAG = REV ? 2 : 1;
+  static_assert(!(REV && SPLIT), "not combined");
   constexpr unsigned ALL = (PY * VX >= 32) ? 0xffffffffu : ((1u << (PY * VX)) - 1u);
   static_assert(KTraits<K>::R == 1 && KTraits<K>::TO == 1, "radius-1, first-order-in-time only");
   static_assert(PY * VX <= 32, "point masks are 32 bits");
@@ -94,6 +134,11 @@ k_r1(const R1Args<R> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // edge[l][parity][warp][0 = first row, 1 = last row][WX]
   R *edge = reinterpret_cast<R *>(smem_raw);
+  unsigned long long *const sbar = reinterpret_cast<unsigned long long *>(smem_raw + Cfg::EDGE_BYTES);
+  if constexpr (SPLIT) {
+    if (threadIdx.x == 0) sb_init(sbar, 32 * NW);
+    __syncthreads();
+  }
   auto edge_ptr = [&](int l, int par, int w, int which) -> R * {
     return edge + ((((size_t)l * 2 + par) * NW + w) * 2 + which) * WX;
   };
@@ -142,7 +187,7 @@ k_r1(const R1Args<R> a) {
   const bool any_part = __any_sync(0xffffffffu, part_rows != 0u);
   const long long row0 = (long long)y0 * g.px + x;   // offset of my first point inside a plane
   const R *const coef_t = a.coef + row0;   // per-thread base; the (z, row) offset below is warp-uniform
-  const int nit = (ze - zb) + 2 * T;
+  const int nit = (ze - zb) + (REV ? 3 * T - 1 : 2 * T);
 
   // The loop body exists twice: FRAME = false for iterations in which this warp cannot see a
   // non-interior point (no pass-through code at all), FRAME = true for warps on the x/y frame and for
@@ -197,6 +242,9 @@ k_r1(const R1Args<R> a) {
     constexpr int iB = PH, iC = (PH + 1) % 3, iF = (PH + 2) % 3;
     const int zin = zb - T + it;
     const int cur = it & 1;
+    // split barrier: everything published in iteration it-1 is visible, and everyone has finished reading the
+    // buffers this iteration overwrites
+    if constexpr (SPLIT) { if (it > 0) sb_wait(sbar, (unsigned)((it - 1) & 1)); }
 
     if constexpr (T == 1) {
       // level 0: take the prefetched plane, keep the prefetch queue full
@@ -214,19 +262,25 @@ k_r1(const R1Args<R> a) {
     }
 
     // publish the first/last row of the level-0 plane for next iteration's level-1 update
-    if constexpr (!(DBG & 2)) {
+    if constexpr (!(DBG & 2) && !REV) {
       st128<R>(edge_ptr(0, cur, warp, 0) + lane * VX, S[0][iF][0]);
       st128<R>(edge_ptr(0, cur, warp, 1) + lane * VX, S[0][iF][PY - 1]);
     }
 
     R Ofin[PY][VX];
-    static_for<0, T>([&](auto level_tag) {
+    auto level = [&](auto level_tag) {
       constexpr int l = decltype(level_tag)::value;
       // level l+1 at plane zc from level l planes zc-1 (B), zc (C), zc+1 (F)
-      const int zc = zin - l - 1;
+      const int zc = zin - LAG * l - 1;
       R (&Bp)[PY][VX] = S[l][iB];
       R (&Cp)[PY][VX] = S[l][iC];
       R (&Fp)[PY][VX] = S[l][iF];
+      // REV: every level publishes the edge rows of its own newest plane (the centre plane of the next
+      // iteration); level 0 does so here too, i.e. at the end of the iteration, after its load has landed
+      if constexpr (REV) {
+        st128<R>(edge_ptr(l, cur, warp, 0) + lane * VX, Fp[0]);
+        st128<R>(edge_ptr(l, cur, warp, 1) + lane * VX, Fp[PY - 1]);
+      }
 
       // rows just outside my strip, owned by the neighbouring warps (written last iteration)
       R up[VX], dn[VX];
@@ -239,6 +293,9 @@ k_r1(const R1Args<R> a) {
           ld128s<R>(edge_ptr(l, cur ^ 1, wu, 1) + lane * VX, up);
           ld128s<R>(edge_ptr(l, cur ^ 1, wd, 0) + lane * VX, dn);
         }
+        // last shared-memory access of this iteration (the edges of levels 1..T-1 were published by the
+        // earlier stages, level T is not exchanged): arrive now, run this level and the stores underneath
+        if constexpr (SPLIT && l == T - 1) sb_arrive(sbar);
       }
 
       auto stage = [&](R (&O)[PY][VX]) {
@@ -287,22 +344,27 @@ k_r1(const R1Args<R> a) {
 #pragma unroll
             for (int e = 0; e < VX; ++e) O[j][e] = ((upd >> (j * VX + e)) & 1u) ? O[j][e] : Cp[j][e];
         }
-        if constexpr (l + 1 < T && !(DBG & 2)) {
+        if constexpr (l + 1 < T && !(DBG & 2) && !REV) {
           st128<R>(edge_ptr(l + 1, cur, warp, 0) + lane * VX, O[0]);
           st128<R>(edge_ptr(l + 1, cur, warp, 1) + lane * VX, O[PY - 1]);
         }
       };
-      if constexpr (l + 1 < T) stage(S[l + 1][iF]);
+      // forward order: the new plane is this iteration's "F" of level l+1.  REV: level l+1 has already run in
+      // this iteration and released its "B" plane, which is next iteration's "F".
+      if constexpr (l + 1 < T) stage(S[l + 1][REV ? iB : iF]);
       else stage(Ofin);
       if constexpr (T > 1 && l == 0) {
-        load_plane(zin + 1, S[0][iB], it + 1 < nit);   // next iteration's level-0 "F"
+        // next iteration's level-0 "F"; REV streams T-1 iterations longer than there are planes to read
+        load_plane(zin + 1, S[0][iB], (it + 1 < nit) && (!REV || zin + 1 < ze + T));
       }
-    });
+    };
+    if constexpr (REV) static_for_rev<T>(level);
+    else static_for<0, T>(level);
 
-    // Ofin is level T at plane zin - T.  Rows whose VX points all lie in the core go out as predicated
+    // Ofin is level T at plane zin - LAG*(T-1) - 1.  Rows whose VX points all lie in the core go out as predicated
     // 128-bit stores (no branches); rows cut by the domain edge (nx not a multiple of VX) are rare and
     // take a warp-uniform slow path.
-    const int zo = zin - T;
+    const int zo = zin - LAG * (T - 1) - 1;
     const bool zst = (zo >= zb) && (zo < ze);
     R *q = a.out + (long long)zo * g.pxy + row0;
     const unsigned fm = zst ? full_rows : 0u;
@@ -320,7 +382,7 @@ k_r1(const R1Args<R> a) {
         }
       }
     }
-    if constexpr (!(DBG & 2)) __syncthreads();
+    if constexpr (!(DBG & 2) && !SPLIT) __syncthreads();
   };
 
   // planes zin-T .. zin-1 are produced in iteration `it`; the version is chosen per iteration
@@ -328,7 +390,7 @@ k_r1(const R1Args<R> a) {
     const int zin = zb - T + it;
     if constexpr (DBG & 8) body(phase_tag, FrameTag<false>{}, it);       // experiment (results invalid)
     else if constexpr (DBG & 16) body(phase_tag, FrameTag<true>{}, it);   // experiment
-    else if (warp_masked || (zin - T < g.zlo) || (zin > g.zhi)) body(phase_tag, FrameTag<true>{}, it);
+    else if (warp_masked || (zin - LAG * (T - 1) - 1 < g.zlo) || (zin > g.zhi)) body(phase_tag, FrameTag<true>{}, it);
     else body(phase_tag, FrameTag<false>{}, it);
   };
   int it = 0;

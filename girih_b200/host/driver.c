@@ -1,7 +1,7 @@
 /*
  * driver.c -- main() of mwd_kernel.  Follows src/driver.c:21-82: defaults -> command line ->
  * topology check -> init -> verify or performance_test.  MPI_Init and the MPI ranks become host
- * threads, one per GPU (--npz), started after the command line has been parsed once.
+ * threads, one per GPU (--npx * --npy * --npz), started after the command line has been parsed once.
  */
 #include <stdlib.h>
 #include <string.h>
@@ -25,11 +25,8 @@ int main(int argc, char **argv) {
   base.mpi_size = 1;
   param_default(&base);
   parse_args(argc, argv, &base);   /* --help / --list / bad flags exit here with status 0 */
-  if (base.t.shape[0] != 1 || base.t.shape[1] != 1) {
-    fprintf(stderr, "ERROR: this build decomposes the domain across the Z direction only (use --npx 1 --npy 1 --npz <GPUs>)\n");
-    return 1;
-  }
-  nranks = base.t.shape[2];
+  nranks = base.t.shape[0] * base.t.shape[1] * base.t.shape[2];
+  if (base.t.shape[0] < 1 || base.t.shape[1] < 1 || base.t.shape[2] < 1) nranks = 0;
   if (nranks < 1) {
     fprintf(stderr, "ERROR: requested MPI topology shape does not match the available processes count: \n\tRequested:%03d \n\tAvailable:%03d\n",
             nranks, 1);

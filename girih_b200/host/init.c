@@ -64,8 +64,9 @@ static void intra_diamond_info_init(Parameters *p) {
 
   if (p->t_dim < 1) girih_fatal(p, "Diamond method does not support unrolling in time less than 1"); /* :1023 */
   if (p->t_dim % 2 == 0) girih_fatal(p, "diamond method does not supports even time unrolling");     /* :1029 */
-  if (p->t.shape[0] > 1 || p->t.shape[1] > 1)
-    girih_fatal(p, "this build decomposes the domain across the Z direction only");
+  if (p->t.shape[0] > 1 || p->t.shape[1] > 1) /* the reference's rule is npx == npz == 1 (:1035-1040); the GPU
+                                                * diamond stepper shards z-slabs instead of y-diamonds */
+    girih_fatal(p, "the Diamond stepper of this build decomposes the domain across the Z direction only (use --npx 1 --npy 1 --npz <GPUs>)");
 
   diam_width = (p->t_dim + 1) * 2 * r;
   diam_concurrency = p->lstencil_shape[1] / diam_width;
@@ -101,12 +102,12 @@ void init(Parameters *p) { /* src/utils.c:317-433 */
   if (p->target_ts < 0 || p->target_ts > 2) girih_fatal(p, "unknown time stepper %d", p->target_ts);
   set_kernels(p);
   p->n_stencils = (uint64_t)p->stencil_shape[0] * p->stencil_shape[1] * p->stencil_shape[2];
-  if (p->t.shape[0] != 1 || p->t.shape[1] != 1)
-    girih_fatal(p, "this build decomposes the domain across the Z direction only (use --npx 1 --npy 1 --npz <GPUs>)");
   if (p->mpi_size == 1 && p->halo_concat == 1) p->halo_concat = 0;
 
-  p->t.rank_coords[0] = p->t.rank_coords[1] = 0;
-  p->t.rank_coords[2] = p->mpi_rank;
+  /* MPI_Cart_create / MPI_Cart_coords (src/mpi_utils.c:74-77): row-major rank order, z fastest */
+  p->t.rank_coords[2] = p->mpi_rank % p->t.shape[2];
+  p->t.rank_coords[1] = (p->mpi_rank / p->t.shape[2]) % p->t.shape[1];
+  p->t.rank_coords[0] = p->mpi_rank / (p->t.shape[2] * p->t.shape[1]);
   for (i = 0; i < 3; i++) { /* :339-356 */
     if (p->t.shape[i] > 1) {
       q = p->stencil_shape[i] / p->t.shape[i];
@@ -124,7 +125,8 @@ void init(Parameters *p) { /* src/utils.c:317-433 */
     }
     p->ge[i] = p->gb[i] + p->lstencil_shape[i] - 1;
   }
-  if (p->lstencil_shape[2] < 1) girih_fatal(p, "more GPUs than z planes");
+  if (p->lstencil_shape[0] < 1 || p->lstencil_shape[1] < 1 || p->lstencil_shape[2] < 1)
+    girih_fatal(p, "more GPUs than grid points along one direction");
 
   if (p->array_padding == 1) { /* :367-374: alignment counts ELEMENTS here */
     if (p->alignment < 1) girih_fatal(p, "alignment must be positive");
@@ -299,11 +301,12 @@ void gpu_attach(Parameters *p) {
     exit(1);
   }
   if (p->mpi_size > ndev)
-    girih_fatal(p, "requested %d GPUs (--npz) but only %d are visible", p->mpi_size, ndev);
+    girih_fatal(p, "requested %d GPUs (--npx * --npy * --npz) but only %d are visible", p->mpi_size, ndev);
   p->gpu_device = p->mpi_rank;
   rc = girih_gpu_create(&p->gpu, p->gpu_device, p->target_kernel, (int)sizeof(real_t), p->lstencil_shape,
                         p->ldomain_shape, p->mpi_rank, p->mpi_size);
   gpu_check(p, rc, "girih_gpu_create");
+  gpu_check(p, girih_gpu_set_topology(p->gpu, p->t.shape, p->t.rank_coords), "girih_gpu_set_topology");
   if (p->mpi_size > 1) {
     memset(id, 0, sizeof(id));
     if (p->mpi_rank == 0) gpu_check(p, girih_gpu_comm_unique_id(id, sizeof(id)), "girih_gpu_comm_unique_id");

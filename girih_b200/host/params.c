@@ -96,7 +96,9 @@ void print_help(Parameters *p) {
         "  --nx <integer>  --ny <integer>  --nz <integer>\n       Global domain size\n"
         "  --nt <integer>\n       Number of time steps\n"
         "  --npx <integer>  --npy <integer>  --npz <integer>\n"
-        "       Process topology. This build decomposes along z only: --npz is the number of GPUs\n"
+        "       Process topology: one GPU per process, npx*npy*npz GPUs.  z-slabs (--npz) are the fast path;\n"
+        "       --npx/--npy > 1 is available for the single-step steppers (ts 0, 1), the Diamond stepper needs\n"
+        "       --npx 1 --npy 1\n"
         "  --n-tests <integer>\n       Repetitions of the time stepper in a performance run\n"
         "  --alignment <integer>\n       Alignment of the allocated host arrays\n"
         "\nDisplay options:\n"

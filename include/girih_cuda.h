@@ -104,6 +104,16 @@ void girih_gpu_destroy(girih_gpu_ctx *ctx);
 int girih_gpu_comm_unique_id(void *id, size_t len);
 int girih_gpu_comm_init(girih_gpu_ctx *ctx, const void *id, size_t len);
 
+/* Process topology (--npx/--npy/--npz; MPI_Cart_create / MPI_Cart_coords / MPI_Cart_shift of
+ * src/mpi_utils.c:63-81): dims = (npx, npy, npz) with npx*npy*npz == nranks, coords = this rank's position,
+ * rank == (coords[0]*npy + coords[1])*npz + coords[2] (MPI's row-major order).  Optional -- without it the ranks
+ * form z-slabs -- and to be called before girih_gpu_comm_init.  With npx or npy > 1 the steppers also exchange the
+ * r-deep x and y faces of src/mpi_utils.c:116-170 after every step (device pack / ncclSend+ncclRecv / unpack, the
+ * analogue of sub_array_copy, src/mpi_utils.c:31-45) and run single steps only: like the reference, whose
+ * diamond stepper rejects an x decomposition (src/kernels/diamond_utils.c:1035-1040), temporal fusion needs
+ * npx == npy == 1 here. */
+int girih_gpu_set_topology(girih_gpu_ctx *ctx, const int dims[3], const int coords[3]);
+
 /* Host -> device of the arrays arrays_allocate()/init_coeff()/domain_data_fill() produced
  * (src/performance.c:50-52).  U3 (roc2) may be NULL unless time_order == 2; coef holds
  * n_coef_scalars values (constant) or n_coef_arrays*ln_domain values (variable), in the

@@ -219,8 +219,22 @@ static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long 
   return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
 
-// cp.async wrappers of kernels_r4.cuh (the product versions are inline PTX)
+// cp.async wrappers of kernels_r4.cuh and the split barrier of kernels_r1.cuh (the product versions are inline PTX)
 namespace girih {
+// mbarrier word: [phase:32][expected:16][pending:16]; all fibers of a CTA run on one OS thread
+static inline void sb_init(unsigned long long *bar, int count) { *bar = ((unsigned long long)count << 16) | (unsigned)count; }
+static inline void sb_arrive(unsigned long long *bar) {
+  unsigned long long v = *bar;
+  const unsigned expected = (unsigned)(v >> 16) & 0xffffu;
+  unsigned pending = (unsigned)v & 0xffffu;
+  unsigned long long phase = v >> 32;
+  if (--pending == 0) { phase++; pending = expected; }
+  *bar = (phase << 32) | ((unsigned long long)expected << 16) | pending;
+  cuda_emu::B->idle = 0;
+}
+static inline void sb_wait(unsigned long long *bar, unsigned parity) {
+  while ((unsigned)((*(volatile unsigned long long *)bar) >> 32 & 1u) == parity) cuda_emu::yield();
+}
 static inline void cp_async16(void *smem, const void *gmem) { cuda_emu::cp_async_issue(smem, gmem); }
 static inline void cp_async_commit() { cuda_emu::cp_async_commit_group(); }
 template <int N> static inline void cp_async_wait() { cuda_emu::cp_async_wait_group(N); }

@@ -7,6 +7,8 @@ This is a checker for the host-side logic and the kernel logic together -- it ne
 GPU run: the product loads libgirih_cuda.so only, and nothing under girih_b200/ knows the emulator
 exists.  Stream/event ordering is not modelled (every operation completes in program order)."""
 import ctypes as C
+import os
+import subprocess
 
 import numpy as np
 import pytest
@@ -27,10 +29,20 @@ def emu_library():
     return _emu
 
 
+def emu_cli(dtype, args, timeout=3600, env=None):
+    """girih_b200/host (the CLI) linked against the emulator library: tests/cuda_emu/_build/mwd_kernel_emu_*"""
+    emu_library()
+    exe = os.path.join(os.path.dirname(E.LIB_PATH), "mwd_kernel_emu_" + ("dp" if np.dtype(dtype).itemsize == 8 else "sp"))
+    out = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=timeout,
+                         env=dict(os.environ, **(env or {})))
+    return out.returncode, out.stdout, out.stderr
+
+
 @pytest.fixture(autouse=True)
 def _route_mirror_to_emulator(monkeypatch):
     monkeypatch.setattr(G.GpuStepper, "_load", staticmethod(emu_library))
     monkeypatch.setattr(G, "gpu_count", lambda: 4)
+    monkeypatch.setattr(G, "run_reference_cli", emu_cli)
     monkeypatch.delenv("CUDA_EMU_SCHED", raising=False)
 
 
@@ -61,3 +73,111 @@ test_repeated_runs_keep_evolving_like_the_reference = P.test_repeated_runs_keep_
 test_frame_mismatch_is_reported = P.test_frame_mismatch_is_reported
 test_scan_counts_nan_and_zero = P.test_scan_counts_nan_and_zero
 test_z_slabs_match_global_oracle = P.test_z_slabs_match_global_oracle
+test_xy_topologies_match_global_oracle = P.test_xy_topologies_match_global_oracle
+test_cli_verify = P.test_cli_verify
+test_cli_verify_contracted = P.test_cli_verify_contracted
+test_cli_autotune_prints_reference_prefix = P.test_cli_autotune_prints_reference_prefix
+
+
+# ------------------------------------------------------------------------------------------------
+# --npx / --npy / --npz topologies (src/mpi_utils.c:63-170): every rank a host thread on the emulator, the
+# assembled sub-domains against the serial oracle on the global domain, as the reference itself
+# verifies decomposed runs (src/verification.c:955-1040)
+# ------------------------------------------------------------------------------------------------
+def _topology_run(kernel, gst, dt, dims, fn):
+    import threading
+    nranks = dims[0] * dims[1] * dims[2]
+    uid = G.GpuStepper.comm_unique_id()
+    out, errs = [None] * nranks, []
+
+    def work(rank):
+        try:
+            pb = G.make_problem(kernel, gst, dt, rank=rank, nranks=nranks, topology=dims)
+            s = G.GpuStepper(kernel, pb.stencil, pb.shape, dt, device=rank % 4, rank=rank, nranks=nranks)
+            s.set_topology(pb.dims, pb.coords)
+            s.comm_init(uid)
+            s.upload(pb)
+            fn(s)
+            s.download(pb.U1, pb.U2)
+            s.close()
+            out[rank] = pb
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    if errs:
+        raise errs[0]
+    return out
+
+
+def _assert_subdomains(slabs, ob, whole_halo=True):
+    r = ob.r
+    for pb in slabs:
+        x0, y0, z0 = pb.gb
+        nx, ny, nz = pb.stencil
+        for mine, ref in ((pb.U1, ob.U1), (pb.U2, ob.U2)):
+            assert np.array_equal(mine[r:r + nz, r:r + ny, r:r + nx],
+                                  ref[z0 + r:z0 + r + nz, y0 + r:y0 + r + ny, x0 + r:x0 + r + nx])
+        if whole_halo:   # halos (faces, edges and corners) of both arrays are current after the run
+            for mine, ref in ((pb.U1, ob.U1), (pb.U2, ob.U2)):
+                assert np.array_equal(mine[:, :, :nx + 2 * r], ref[z0:z0 + nz + 2 * r, y0:y0 + ny + 2 * r, x0:x0 + nx + 2 * r])
+
+
+@pytest.mark.parametrize("dims", [(2, 1, 1), (1, 2, 1), (2, 2, 1), (2, 1, 2), (1, 3, 2), (2, 2, 2), (3, 1, 1)])
+@pytest.mark.parametrize("kernel", [0, 1, 4, 5, 7])
+def test_xyz_topologies_match_global_oracle(oracle, kernel, dims):
+    gst, nsteps = (37, 29, 23), 6
+    for dt in (np.float64, np.float32):
+        for ts in (0, 1):
+            slabs = _topology_run(kernel, gst, dt, dims, lambda s: s.run_single(nsteps, overlap=bool(ts)))
+            ob = oracle.make_problem(kernel, gst, dt)
+            oracle.run_steps(ob, nsteps)
+            _assert_subdomains(slabs, ob)
+
+
+def test_fused_stepper_falls_back_to_single_steps_on_xy_topologies(oracle):
+    gst, nsteps = (40, 32, 24), 9
+    infos = []
+
+    def fn(s):
+        s.run_fused(nsteps, 4)
+        infos.append(s.launch_info())
+
+    slabs = _topology_run(1, gst, np.float64, (2, 2, 1), fn)
+    assert all(i["tfuse"] == 1 and i["steps"] == nsteps for i in infos)
+    ob = oracle.make_problem(1, gst, np.float64)
+    oracle.run_steps(ob, nsteps)
+    _assert_subdomains(slabs, ob)
+
+
+def test_topology_argument_checks():
+    pb = G.make_problem(1, (16, 16, 16), np.float64, rank=1, nranks=4, topology=(2, 2, 1))
+    assert pb.coords == (0, 1, 0) and pb.stencil == (8, 8, 16) and pb.gb == (0, 8, 0)
+    s = G.GpuStepper(1, pb.stencil, pb.shape, np.float64, device=0, rank=1, nranks=4)
+    with pytest.raises(G.GirihError):
+        s.set_topology((2, 2, 2), (0, 1, 0))      # product != nranks
+    with pytest.raises(G.GirihError):
+        s.set_topology((2, 2, 1), (1, 0, 0))      # coordinates of another rank
+    s.set_topology((2, 2, 1), (0, 1, 0))
+    s.close()
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("top", [(2, 1, 1), (1, 2, 1), (2, 2, 2), (1, 1, 3), (3, 2, 1)])
+@pytest.mark.parametrize("ts,kernel", [(0, 1), (1, 0), (0, 4), (1, 7)])
+def test_cli_verify_topologies(ts, kernel, top, dt):
+    """mwd_kernel --npx/--npy/--npz --verify 1: the reference's verdict line (src/verification.c:851-852) from
+    one rank thread per (emulated) GPU"""
+    rc, out, err = emu_cli(dt, ["--nx", 48, "--ny", 36, "--nz", 30, "--nt", 10, "--target-ts", ts, "--target-kernel", kernel,
+                                "--verify", 1, "--verbose", 0, "--npx", top[0], "--npy", top[1], "--npz", top[2]])
+    assert rc == 0, out + err
+    assert "eMax:0.000e+00|eL1:0.000e+00-PASSED" in out
+    assert "top:(%d,%d,%d)" % top in out
+
+
+def test_cli_diamond_rejects_xy_topologies():
+    rc, out, err = emu_cli(np.float64, ["--nx", 48, "--ny", 32, "--nz", 40, "--nt", 20, "--target-ts", 2, "--target-kernel", 1,
+                                        "--t-dim", 3, "--verify", 1, "--npx", 2])
+    assert rc == 1 and "ERROR: the Diamond stepper of this build decomposes the domain across the Z direction only" in err

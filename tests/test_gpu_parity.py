@@ -413,14 +413,16 @@ def test_cli_performance_schema():
 # ------------------------------------------------------------------------------------------------
 # multi-GPU (needs >= 2 devices; one host thread per GPU like mwd_kernel --npz)
 # ------------------------------------------------------------------------------------------------
-def _multi_gpu_run(kernel, gst, dt, nranks, fn):
+def _multi_gpu_run(kernel, gst, dt, nranks, fn, topology=None):
     uid = G.GpuStepper.comm_unique_id()
     out, errs = [None] * nranks, []
 
     def work(rank):
         try:
-            pb = G.make_problem(kernel, gst, dt, rank=rank, nranks=nranks)
+            pb = G.make_problem(kernel, gst, dt, rank=rank, nranks=nranks, topology=topology)
             s = G.GpuStepper(kernel, pb.stencil, pb.shape, dt, device=rank, rank=rank, nranks=nranks)
+            if topology is not None:
+                s.set_topology(pb.dims, pb.coords)
             s.comm_init(uid)
             s.upload(pb)
             fn(s)
@@ -463,3 +465,25 @@ def test_z_slabs_match_global_oracle(oracle, kernel, tfuse):
             assert np.array_equal(pb.U1[r:r + lnz], ob.U1[z0 + r:z0 + r + lnz])
             assert np.array_equal(pb.U2[r:r + lnz], ob.U2[z0 + r:z0 + r + lnz])
             assert np.array_equal(pb.U1, ob.U1[z0:z0 + lnz + 2 * r])
+
+
+@pytest.mark.parametrize("dims", [(2, 1, 1), (1, 2, 1), (2, 2, 1), (2, 1, 2), (2, 2, 2)])
+@pytest.mark.parametrize("kernel", [0, 1, 5, 7])
+def test_xy_topologies_match_global_oracle(oracle, kernel, dims):
+    """--npx/--npy/--npz for the single-step steppers (src/mpi_utils.c:63-170): r-deep x, y and z faces after every
+    step; sub-domains, including their halos (faces, edges, corners), against the serial global oracle"""
+    n = dims[0] * dims[1] * dims[2]
+    if G.gpu_count() < n:
+        pytest.skip(f"needs >= {n} GPUs")
+    gst, nsteps, dt = (37, 29, 23), 6, np.float64
+    for ts in (0, 1):
+        slabs = _multi_gpu_run(kernel, gst, dt, n, lambda s: s.run_single(nsteps, overlap=bool(ts)), topology=dims)
+        ob = oracle.make_problem(kernel, gst, dt)
+        oracle.run_steps(ob, nsteps)
+        r = ob.r
+        for pb in slabs:
+            x0, y0, z0 = pb.gb
+            nx, ny, nz = pb.stencil
+            for mine, ref in ((pb.U1, ob.U1), (pb.U2, ob.U2)):
+                assert np.array_equal(mine[:, :, :nx + 2 * r],
+                                      ref[z0:z0 + nz + 2 * r, y0:y0 + ny + 2 * r, x0:x0 + nx + 2 * r])
