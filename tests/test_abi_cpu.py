@@ -114,7 +114,8 @@ def test_cli_list_and_help_match_reference_behaviour(oracle):
     rc, out, err = G.run_reference_cli(np.float32, ["--target-ts", 2, "--target-kernel", 1, "--t-dim", 2,
                                                     "--nx", 32, "--ny", 32, "--nz", 32])
     assert rc == 1 and "even time unrolling" in err         # diamond_utils.c:1029
-    rc, out, err = G.run_reference_cli(np.float32, ["--npx", 2])
+    rc, out, err = G.run_reference_cli(np.float32, ["--npx", 2, "--target-ts", 2, "--target-kernel", 1, "--t-dim", 1,
+                                                    "--nx", 32, "--ny", 32, "--nz", 32])   # Diamond: z-slabs only
     assert rc == 1 and "Z direction only" in err
     if G.gpu_count() == 0:
         rc, out, err = G.run_reference_cli(np.float32, ["--nx", 16, "--ny", 16, "--nz", 16, "--verbose", 0])
