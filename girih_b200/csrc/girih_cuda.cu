@@ -995,8 +995,9 @@ static std::vector<int> tile_candidates(const girih_gpu_ctx *c, int T) {
     if (c->opt_variant == 2) return {216, 408};
     return {0, 108, 208, 404, 408};
   }
-  if (c->opt_contract) return {0};
-  if (c->kernel == 1) return {216, 408, 312, 310, 316};
+  // 5xxx = split-barrier variants (profiles/kernel_sweep_r01.md, round 1b: +3..8% at T = 2, 3 and in fp32)
+  if (c->opt_contract) return c->kernel == 1 ? std::vector<int>{0, 5408, 5216} : std::vector<int>{0};
+  if (c->kernel == 1) return {216, 408, 312, 310, 316, 5408, 5216};
   return {216, 408};
 }
 
