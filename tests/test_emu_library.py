@@ -74,6 +74,7 @@ test_frame_mismatch_is_reported = P.test_frame_mismatch_is_reported
 test_scan_counts_nan_and_zero = P.test_scan_counts_nan_and_zero
 test_z_slabs_match_global_oracle = P.test_z_slabs_match_global_oracle
 test_xy_topologies_match_global_oracle = P.test_xy_topologies_match_global_oracle
+test_autotune_then_results_are_unchanged = P.test_autotune_then_results_are_unchanged
 test_cli_verify = P.test_cli_verify
 test_cli_verify_contracted = P.test_cli_verify_contracted
 test_cli_autotune_prints_reference_prefix = P.test_cli_autotune_prints_reference_prefix
