@@ -807,7 +807,9 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
       if ((rc = timed_exchange(c, c->dU[src], T * r))) return rc;
     }
     const int nd = (p + 1 < sizes.size()) ? sizes[p + 1] * r : r;   // halo depth the next pass needs
-    if (overlap && c->nranks > 1 && g.nz >= 4 * nd) {
+    // (decided on the thinnest slab of the run so that every rank takes the same branch: the two branches
+    // exchange at different points)
+    if (overlap && c->nranks > 1 && c->nz_min >= 4 * nd) {
       // the two outer quarters of the slab first (one launch, full waves: thin boundary launches would pay
       // the 2T-plane pipeline fill for a few planes), then the halo exchange of the new level runs under
       // the sweep of the inner half
@@ -917,7 +919,7 @@ extern "C" int girih_gpu_run_fused(girih_gpu_ctx *c, int nsteps, int tfuse) {
   if (T <= 0) T = c->tuned_tfuse > 0 ? c->tuned_tfuse : default_tfuse(c);
   T = std::min(T, c->kd.max_tfuse);
   if (c->opt_variant == 1 || c->kernel == 7 || xy_decomposed(c)) T = 1;
-  if (c->nranks > 1) T = std::min(T, std::max(1, c->g.nz / std::max(1, c->g.r)));
+  if (c->nranks > 1) T = std::min(T, std::max(1, c->nz_min / std::max(1, c->g.r)));   // same depth on every rank
   if (T > 1 && !c->frames_equal) return fail(c, GIRIH_ERR_FRAME, "%s", girih_gpu_strerror(GIRIH_ERR_FRAME));
   int rc;
   if ((rc = begin_run(c))) return rc;
@@ -1009,7 +1011,7 @@ extern "C" int girih_gpu_autotune(girih_gpu_ctx *c, int fused, int verbose, int 
   const double lups = (double)c->g.nx * c->g.ny * c->g.nz;
   int Tmax = fused ? c->kd.max_tfuse : 1;
   if (c->opt_variant == 1 || c->kernel == 7 || !c->frames_equal) Tmax = 1;
-  if (c->nranks > 1) Tmax = std::min(Tmax, std::max(1, c->g.nz / std::max(1, c->g.r)));
+  if (c->nranks > 1) Tmax = std::min(Tmax, std::max(1, c->nz_min / std::max(1, c->g.r)));
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0));
   CU(cudaEventCreate(&e1));

@@ -41,7 +41,7 @@ def emu_cli(dtype, args, timeout=3600, env=None):
 @pytest.fixture(autouse=True)
 def _route_mirror_to_emulator(monkeypatch):
     monkeypatch.setattr(G.GpuStepper, "_load", staticmethod(emu_library))
-    monkeypatch.setattr(G, "gpu_count", lambda: 4)
+    monkeypatch.setattr(G, "gpu_count", lambda: 5)
     monkeypatch.setattr(G, "run_reference_cli", emu_cli)
     monkeypatch.delenv("CUDA_EMU_SCHED", raising=False)
 
@@ -75,6 +75,7 @@ test_scan_counts_nan_and_zero = P.test_scan_counts_nan_and_zero
 test_z_slabs_match_global_oracle = P.test_z_slabs_match_global_oracle
 test_xy_topologies_match_global_oracle = P.test_xy_topologies_match_global_oracle
 test_autotune_then_results_are_unchanged = P.test_autotune_then_results_are_unchanged
+test_overlap_with_uneven_slabs_takes_one_schedule_on_every_rank = P.test_overlap_with_uneven_slabs_takes_one_schedule_on_every_rank
 test_cli_verify = P.test_cli_verify
 test_cli_verify_contracted = P.test_cli_verify_contracted
 test_cli_autotune_prints_reference_prefix = P.test_cli_autotune_prints_reference_prefix

@@ -487,3 +487,21 @@ def test_xy_topologies_match_global_oracle(oracle, kernel, dims):
             for mine, ref in ((pb.U1, ob.U1), (pb.U2, ob.U2)):
                 assert np.array_equal(mine[:, :, :nx + 2 * r],
                                       ref[z0:z0 + nz + 2 * r, y0:y0 + ny + 2 * r, x0:x0 + nx + 2 * r])
+
+
+def test_overlap_with_uneven_slabs_takes_one_schedule_on_every_rank(oracle):
+    """slabs of 16/15/15 planes, r = 4: the halo-first variant needs 4*r planes -- the decision must be taken on
+    the thinnest slab, or the ranks exchange at different points of the step and wait for each other forever
+    (found by tests/cuda_emu/fuzz.py)"""
+    n = 3
+    if G.gpu_count() < n:
+        pytest.skip("needs >= 3 GPUs")
+    for kernel, gst in ((0, (7, 5, 46)), (7, (65, 24, 19))):
+        nr = n if kernel == 0 else min(G.gpu_count(), 5)
+        slabs = _multi_gpu_run(kernel, gst, np.float64, nr, lambda s: (s.set_option("overlap", 1), s.run_fused(3, 3)))
+        ob = oracle.make_problem(kernel, gst, np.float64)
+        oracle.run_steps(ob, 3)
+        r = ob.r
+        for pb in slabs:
+            z0, lnz = pb.gb[2], pb.stencil[2]
+            assert np.array_equal(pb.U1[r:r + lnz], ob.U1[z0 + r:z0 + r + lnz])
