@@ -197,6 +197,23 @@ class GpuStepper:
             self._ctx, U1.ctypes.data if U1 is not None else None,
             U2.ctypes.data if U2 is not None else None), "girih_gpu_download")
 
+    # pipelined transfers for a stream of independent jobs (see include/girih_cuda.h)
+    def prefetch_fields(self, U1, U2):
+        self._check(self._lib.girih_gpu_prefetch_fields(
+            self._ctx, U1.ctypes.data if U1 is not None else None,
+            U2.ctypes.data if U2 is not None else None), "girih_gpu_prefetch_fields")
+
+    def commit_fields(self):
+        self._check(self._lib.girih_gpu_commit_fields(self._ctx), "girih_gpu_commit_fields")
+
+    def download_async(self, U1=None, U2=None):
+        self._check(self._lib.girih_gpu_download_async(
+            self._ctx, U1.ctypes.data if U1 is not None else None,
+            U2.ctypes.data if U2 is not None else None), "girih_gpu_download_async")
+
+    def sync_transfers(self):
+        self._check(self._lib.girih_gpu_sync_transfers(self._ctx), "girih_gpu_sync_transfers")
+
     # -- steppers -----------------------------------------------------------------------------
     def run_single(self, nsteps, overlap=False):
         self._check(self._lib.girih_gpu_run_single(self._ctx, nsteps, int(overlap)), "girih_gpu_run_single")

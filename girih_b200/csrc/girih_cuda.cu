@@ -100,6 +100,12 @@ struct girih_gpu_ctx {
   int tuned_tfuse = 0;                            // 0 = built-in default depth
   unsigned long long *d_scan = nullptr;
   void *d_stage = nullptr;            // linear copy of one host array (fast-path transfers)
+  // pipelined transfers (girih_gpu_prefetch_fields ... girih_gpu_sync_transfers): staging per array and direction,
+  // one stream per copy direction, events that hand the staging buffers back and forth with the compute stream
+  void *d_in[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr};
+  bool in_pending[2] = {false, false};
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_in_ready = nullptr, ev_in_free = nullptr, ev_out_ready = nullptr, ev_out_free = nullptr;
   char err[512] = "";
 };
 
@@ -229,6 +235,16 @@ extern "C" void girih_gpu_destroy(girih_gpu_ctx *c) {
   if (c->d_scan) cudaFree(c->d_scan);
   if (c->d_stage) cudaFree(c->d_stage);
   if (c->d_pack) cudaFree(c->d_pack);
+  if (c->s_h2d) cudaStreamSynchronize(c->s_h2d);
+  if (c->s_d2h) cudaStreamSynchronize(c->s_d2h);
+  for (int i = 0; i < 2; ++i) {
+    if (c->d_in[i]) cudaFree(c->d_in[i]);
+    if (c->d_out[i]) cudaFree(c->d_out[i]);
+  }
+  for (cudaEvent_t ev : {c->ev_in_ready, c->ev_in_free, c->ev_out_ready, c->ev_out_free})
+    if (ev) cudaEventDestroy(ev);
+  if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
   for (auto &p : c->comm_ev) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
@@ -413,6 +429,105 @@ extern "C" int girih_gpu_download(girih_gpu_ctx *c, void *U1, void *U2) {
   if (U1 && (rc = fast_copy(c, c->dU[0], U1, false))) return rc;
   if (U2 && (rc = fast_copy(c, c->dU[1], U2, false))) return rc;
   CU(cudaStreamSynchronize(c->s_comp));
+  return GIRIH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pipelined transfers for a stream of independent jobs on one context.  The copies of job i+1 (host -> device)
+// and of job i-1 (device -> host) run on their own streams, i.e. on the two copy engines, underneath the
+// sweeps of job i; the layout conversions stay on the compute stream (0.4 ms per array at 512^3).
+//   prefetch_fields  asynchronous DMA of the next job's fields into staging (page-locked host arrays, valid
+//                    until commit_fields returns)
+//   commit_fields    the prefetched fields become the device arrays (ordered behind the DMA; the staging
+//                    buffers are handed back to the next prefetch by an event)
+//   download_async   layout conversion on the compute stream, then asynchronous DMA to the host
+//   sync_transfers   blocks until every transfer issued so far has completed
+// ------------------------------------------------------------------------------------------------
+static int ensure_pipeline(girih_gpu_ctx *c) {
+  if (c->s_h2d) return GIRIH_OK;
+  CU(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_in_ready, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_in_free, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_out_ready, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_out_free, cudaEventDisableTiming));
+  return GIRIH_OK;
+}
+
+static cudaError_t launch_repitch(girih_gpu_ctx *c, void *dev, void *lin, bool to_device) {
+  const int grid = 148 * 16, hx = c->hshape[0], hy = c->hshape[1], hz = c->hshape[2];
+  if (c->es == 8) {
+    if (to_device) { auto k = k_repitch<double, true>; GIRIH_LAUNCH(k, grid, 256, 0, c->s_comp, c->g, (double *)dev, (double *)lin, hx, hy, hz); }
+    else { auto k = k_repitch<double, false>; GIRIH_LAUNCH(k, grid, 256, 0, c->s_comp, c->g, (double *)dev, (double *)lin, hx, hy, hz); }
+  } else {
+    if (to_device) { auto k = k_repitch<float, true>; GIRIH_LAUNCH(k, grid, 256, 0, c->s_comp, c->g, (float *)dev, (float *)lin, hx, hy, hz); }
+    else { auto k = k_repitch<float, false>; GIRIH_LAUNCH(k, grid, 256, 0, c->s_comp, c->g, (float *)dev, (float *)lin, hx, hy, hz); }
+  }
+  return cudaGetLastError();
+}
+
+extern "C" int girih_gpu_prefetch_fields(girih_gpu_ctx *c, const void *U1, const void *U2) {
+  if (!c || !c->uploaded) return fail(c, GIRIH_ERR_STATE, "prefetch_fields before upload");
+  CU(cudaSetDevice(c->device));
+  int rc = ensure_pipeline(c);
+  if (rc) return rc;
+  const size_t bytes = (size_t)c->hshape[0] * c->hshape[1] * c->hshape[2] * c->es;
+  const void *host[2] = {U1, U2};
+  CU(cudaStreamWaitEvent(c->s_h2d, c->ev_in_free, 0));   // the previous commit has drained the staging buffers
+  for (int i = 0; i < 2; ++i) {
+    c->in_pending[i] = host[i] != nullptr;
+    if (!host[i]) continue;
+    if (!c->d_in[i]) CU(cudaMalloc(&c->d_in[i], bytes));
+    CU(cudaMemcpyAsync(c->d_in[i], host[i], bytes, cudaMemcpyHostToDevice, c->s_h2d));
+  }
+  CU(cudaEventRecord(c->ev_in_ready, c->s_h2d));
+  return GIRIH_OK;
+}
+
+extern "C" int girih_gpu_commit_fields(girih_gpu_ctx *c) {
+  if (!c || !c->uploaded) return fail(c, GIRIH_ERR_STATE, "commit_fields before upload");
+  if (!c->s_h2d) return fail(c, GIRIH_ERR_STATE, "commit_fields without prefetch_fields");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamWaitEvent(c->s_comp, c->ev_in_ready, 0));
+  for (int i = 0; i < 2; ++i) {
+    if (!c->in_pending[i]) continue;
+    CU(launch_repitch(c, c->dU[i], c->d_in[i], true));
+    c->in_pending[i] = false;
+  }
+  CU(cudaEventRecord(c->ev_in_free, c->s_comp));
+  return GIRIH_OK;
+}
+
+extern "C" int girih_gpu_download_async(girih_gpu_ctx *c, void *U1, void *U2) {
+  if (!c || !c->uploaded) return fail(c, GIRIH_ERR_STATE, "download before upload");
+  CU(cudaSetDevice(c->device));
+  int rc = ensure_pipeline(c);
+  if (rc) return rc;
+  const size_t bytes = (size_t)c->hshape[0] * c->hshape[1] * c->hshape[2] * c->es;
+  void *host[2] = {U1, U2};
+  CU(cudaStreamWaitEvent(c->s_comp, c->ev_out_free, 0));   // the previous download has left the staging buffers
+  for (int i = 0; i < 2; ++i) {
+    if (!host[i]) continue;
+    if (!c->d_out[i]) {
+      CU(cudaMalloc(&c->d_out[i], bytes));
+      CU(cudaMemsetAsync(c->d_out[i], 0, bytes, c->s_comp));   // the x padding columns travel as zeros
+    }
+    CU(launch_repitch(c, c->dU[i], c->d_out[i], false));
+  }
+  CU(cudaEventRecord(c->ev_out_ready, c->s_comp));
+  CU(cudaStreamWaitEvent(c->s_d2h, c->ev_out_ready, 0));
+  for (int i = 0; i < 2; ++i)
+    if (host[i]) CU(cudaMemcpyAsync(host[i], c->d_out[i], bytes, cudaMemcpyDeviceToHost, c->s_d2h));
+  CU(cudaEventRecord(c->ev_out_free, c->s_d2h));
+  return GIRIH_OK;
+}
+
+extern "C" int girih_gpu_sync_transfers(girih_gpu_ctx *c) {
+  if (!c) return GIRIH_ERR_ARG;
+  CU(cudaSetDevice(c->device));
+  if (c->s_h2d) CU(cudaStreamSynchronize(c->s_h2d));
+  CU(cudaStreamSynchronize(c->s_comp));
+  if (c->s_d2h) CU(cudaStreamSynchronize(c->s_d2h));
   return GIRIH_OK;
 }
 

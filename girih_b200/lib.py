@@ -14,7 +14,8 @@ HOST_LIBS = {4: os.path.join(PKG, "libgirih_host_sp.so"), 8: os.path.join(PKG, "
 ABI_SYMBOLS = [
     "girih_kernel_count", "girih_kernel_info", "girih_gpu_count", "girih_gpu_create", "girih_gpu_destroy",
     "girih_gpu_comm_unique_id", "girih_gpu_comm_init", "girih_gpu_set_topology", "girih_gpu_upload", "girih_gpu_download",
-    "girih_gpu_upload_fields", "girih_gpu_run_single", "girih_gpu_run_fused", "girih_gpu_step_box",
+    "girih_gpu_upload_fields", "girih_gpu_prefetch_fields", "girih_gpu_commit_fields", "girih_gpu_download_async",
+    "girih_gpu_sync_transfers", "girih_gpu_run_single", "girih_gpu_run_fused", "girih_gpu_step_box",
     "girih_gpu_time_pass", "girih_gpu_last_elapsed_ms", "girih_gpu_last_launch_info", "girih_gpu_scan_u1", "girih_gpu_set_option",
     "girih_gpu_autotune",
     "girih_gpu_strerror", "girih_gpu_last_error", "girih_plan_fused_passes", "girih_plan_halo_exchange", "girih_plan_fused_exchanges",
@@ -56,6 +57,10 @@ def declare(lib: C.CDLL) -> C.CDLL:
     lib.girih_gpu_upload.argtypes = [P, P, P, P, P]
     lib.girih_gpu_download.argtypes = [P, P, P]
     lib.girih_gpu_upload_fields.argtypes = [P, P, P]
+    lib.girih_gpu_prefetch_fields.argtypes = [P, P, P]
+    lib.girih_gpu_commit_fields.argtypes = [P]
+    lib.girih_gpu_download_async.argtypes = [P, P, P]
+    lib.girih_gpu_sync_transfers.argtypes = [P]
     lib.girih_gpu_run_single.argtypes = [P, I, I]
     lib.girih_gpu_run_fused.argtypes = [P, I, I]
     lib.girih_gpu_step_box.argtypes = [P, I, I, I, I, I, I, I]

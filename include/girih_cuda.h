@@ -126,6 +126,19 @@ int girih_gpu_download(girih_gpu_ctx *ctx, void *U1, void *U2);
 /* Same transfers from/to page-locked host memory, asynchronous on the context's stream and
  * followed by a stream synchronise -- used for end-to-end timing. */
 int girih_gpu_upload_fields(girih_gpu_ctx *ctx, const void *U1, const void *U2);
+/* Pipelined transfers for a stream of independent jobs (performance_test()'s n_tests loop with fresh inputs, a
+ * parameter sweep, shots of a survey): the host -> device copy of job i+1 and the device -> host copy of job i-1
+ * run on their own streams (the two copy engines) underneath the sweeps of job i.
+ *   prefetch_fields  asynchronous copy of U1 and/or U2 (page-locked, either may be NULL) into device staging; the
+ *                    host arrays must stay valid until the next stepper call or girih_gpu_sync_transfers returns
+ *   commit_fields    the prefetched fields become the device arrays (stream-ordered behind the copy)
+ *   download_async   like girih_gpu_download, but returns once the copy is enqueued
+ *   sync_transfers   blocks until every transfer issued so far has completed
+ * Typical loop: prefetch(job 0); for i: commit(); prefetch(job i+1); run; download_async(out i); sync_transfers(). */
+int girih_gpu_prefetch_fields(girih_gpu_ctx *ctx, const void *U1, const void *U2);
+int girih_gpu_commit_fields(girih_gpu_ctx *ctx);
+int girih_gpu_download_async(girih_gpu_ctx *ctx, void *U1, void *U2);
+int girih_gpu_sync_transfers(girih_gpu_ctx *ctx);
 
 /*
  * Time steppers.  All follow the reference's parity convention: global step s = 1,2,... reads

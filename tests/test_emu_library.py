@@ -76,6 +76,7 @@ test_z_slabs_match_global_oracle = P.test_z_slabs_match_global_oracle
 test_xy_topologies_match_global_oracle = P.test_xy_topologies_match_global_oracle
 test_autotune_then_results_are_unchanged = P.test_autotune_then_results_are_unchanged
 test_overlap_with_uneven_slabs_takes_one_schedule_on_every_rank = P.test_overlap_with_uneven_slabs_takes_one_schedule_on_every_rank
+test_pipelined_transfers_keep_jobs_apart = P.test_pipelined_transfers_keep_jobs_apart
 test_cli_verify = P.test_cli_verify
 test_cli_verify_contracted = P.test_cli_verify_contracted
 test_cli_autotune_prints_reference_prefix = P.test_cli_autotune_prints_reference_prefix

@@ -505,3 +505,39 @@ def test_overlap_with_uneven_slabs_takes_one_schedule_on_every_rank(oracle):
         for pb in slabs:
             z0, lnz = pb.gb[2], pb.stencil[2]
             assert np.array_equal(pb.U1[r:r + lnz], ob.U1[z0 + r:z0 + r + lnz])
+
+
+@pytest.mark.parametrize("kernel,dt,tfuse", [(1, np.float64, 4), (1, np.float32, 3), (0, np.float64, 1), (5, np.float32, 2)])
+def test_pipelined_transfers_keep_jobs_apart(oracle, kernel, dt, tfuse):
+    """prefetch / commit / download_async over a stream of jobs with DIFFERENT inputs: every job's output equals the
+    oracle run from that job's input (a staging buffer handed over too early, or a copy overtaking a sweep, would
+    mix two jobs)"""
+    st, nsteps, njobs = (70, 41, 29), 9, 5
+    base = G.make_problem(kernel, st, dt)
+    r = base.r
+    s = G.GpuStepper.for_problem(base)
+    jobs = []
+    for j in range(njobs):   # interior scaled per job; the Dirichlet frame stays common to U1 and U2
+        u = base.U2.copy()
+        u[r:-r, r:-r, r:r + st[0]] *= dt(1.0 + 0.125 * j)
+        jobs.append(u)
+    outs = [np.empty_like(base.U1) for _ in range(njobs)]
+    outs2 = [np.empty_like(base.U1) for _ in range(njobs)]
+    # second order in time reads U1 as level -1: such a job brings both arrays
+    u1_in = base.U1.copy() if G.kernel_info(kernel).time_order == 2 else None
+    s.prefetch_fields(u1_in, jobs[0])
+    for j in range(njobs):
+        s.commit_fields()
+        if j + 1 < njobs:
+            s.prefetch_fields(u1_in, jobs[j + 1])
+        s.run_fused(nsteps, tfuse)
+        s.download_async(outs[j], outs2[j] if j % 2 else None)
+    s.sync_transfers()
+    s.close()
+    for j in range(njobs):
+        ob = oracle.make_problem(kernel, st, dt)
+        ob.U2[...] = jobs[j]
+        oracle.run_steps(ob, nsteps)
+        assert outs[j].tobytes() == ob.U1.tobytes(), f"job {j}: U1"
+        if j % 2:
+            assert outs2[j].tobytes() == ob.U2.tobytes(), f"job {j}: U2"

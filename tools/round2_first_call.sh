@@ -11,6 +11,7 @@ nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_rea
 SMI=$!
 python bench.py > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err
 python bench.py --arith contract > gpurun_out/r2_bench_contract.json 2>> gpurun_out/r2_bench.err
+python bench.py --e2e-mode pipelined --no-cpu-baseline > gpurun_out/r2_bench_e2e_pipelined.json 2>> gpurun_out/r2_bench.err
 kill $SMI
 # default tiles vs split barrier (5xxx) vs decoupled levels (7xxx), then every tile through the sweep tool
 python tools/split_bench.py > gpurun_out/r2_sweep_schedules.log 2>&1
