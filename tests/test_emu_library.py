@@ -43,6 +43,7 @@ def _route_mirror_to_emulator(monkeypatch):
     monkeypatch.setattr(G.GpuStepper, "_load", staticmethod(emu_library))
     monkeypatch.setattr(G, "gpu_count", lambda: 5)
     monkeypatch.setattr(G, "run_reference_cli", emu_cli)
+    monkeypatch.setenv("GIRIH_RUN_UNVALIDATED", "1")   # tests that wait for their first hardware run do run here
     monkeypatch.delenv("CUDA_EMU_SCHED", raising=False)
 
 

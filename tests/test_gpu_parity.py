@@ -511,7 +511,11 @@ def test_overlap_with_uneven_slabs_takes_one_schedule_on_every_rank(oracle):
 def test_pipelined_transfers_keep_jobs_apart(oracle, kernel, dt, tfuse):
     """prefetch / commit / download_async over a stream of jobs with DIFFERENT inputs: every job's output equals the
     oracle run from that job's input (a staging buffer handed over too early, or a copy overtaking a sweep, would
-    mix two jobs)"""
+    mix two jobs).  The stream/event hand-over of this path has only run on the CPU emulator so far (which executes in
+    program order): until its first run on hardware it is opt-in here, GIRIH_RUN_UNVALIDATED=1 (tools/round2_first_call.sh
+    sets it), so that an ordering mistake cannot take the rest of the GPU suite down with it."""
+    if os.environ.get("GIRIH_RUN_UNVALIDATED") != "1":
+        pytest.skip("first hardware run pending: set GIRIH_RUN_UNVALIDATED=1")
     st, nsteps, njobs = (70, 41, 29), 9, 5
     base = G.make_problem(kernel, st, dt)
     r = base.r

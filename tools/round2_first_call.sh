@@ -6,6 +6,7 @@
 set -u
 mkdir -p gpurun_out
 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 > gpurun_out/r2_pytest_gpu.log
+GIRIH_RUN_UNVALIDATED=1 python -m pytest tests -q -m gpu -k pipelined 2>&1 | tail -5 > gpurun_out/r2_pytest_unvalidated.log
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap \
   --format=csv -lms 200 > gpurun_out/r2_clocks.csv &
 SMI=$!
