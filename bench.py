@@ -236,6 +236,15 @@ def main_ours(args):
         obj = [G.GpuStepper.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(obj, src=0)
         s.comm_init(obj[0])
+        if args.halo_push:
+            # halo push over NVLink peer memory: every rank maps its z neighbours' arrays (CUDA IPC between processes)
+            blobs = [None] * world
+            dist.all_gather_object(blobs, s.peer_export())
+            if rank > 0:
+                s.peer_attach(0, blobs[rank - 1])
+            if rank + 1 < world:
+                s.peer_attach(1, blobs[rank + 1])
+            s.set_option("halo_push", 1)
     s.upload(pb)
     contract = int(args.arith == "contract")
     s.set_option("contract", contract)
@@ -373,6 +382,9 @@ def main_ours(args):
             except Exception as e:   # noqa: BLE001
                 cpu_base = {"value": None, "unit": "GLUP/s", "cores": host_threads(), "kind": "reference",
                             "sample": f"failed: {e}"}
+    if world > 1 and args.halo_push:   # importers unmap before any exporter frees
+        s.peer_detach()
+        barrier()
     s.close()
     if world > 1:
         dist.barrier()
@@ -392,7 +404,8 @@ def main_ours(args):
                        "halo_exchange": (None if world == 1 else
                                          {"ms_per_step_max_over_ranks": comm_ms / args.steps,
                                           "compute_ms_per_step_per_rank": per_rank_compute,
-                                          "overlap_with_interior": bool(args.overlap)}),
+                                          "overlap_with_interior": bool(args.overlap),
+                                          "halo_push": bool(args.halo_push)}),
                        "wall_s": wall},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "GLUP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -417,6 +430,10 @@ def main():
                     help="strict = library default (no FMA); contract = FMA pattern of the reference built with -mfma")
     ap.add_argument("--ref-nz", type=int, default=512, help="z extent of the bounded CPU sample")
     ap.add_argument("--ref-nt", type=int, default=500, help="time steps of the bounded CPU sample")
+    ap.add_argument("--halo-push", type=int, default=0,
+                    help="N>1: fused passes store their boundary planes straight into the neighbours' halos over NVLink "
+                         "(girih_gpu_peer_export/_attach, option halo_push) instead of NCCL exchanges between passes; "
+                         "opt-in until validated on hardware")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-mode", default="sequential", choices=["sequential", "pipelined"],
                     help="sequential: H2D, stepper, D2H one after the other for every step (default). pipelined: the steps "

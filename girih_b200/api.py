@@ -176,6 +176,18 @@ class GpuStepper:
         """(npx, npy, npz) and this rank's position; before comm_init.  Default: z-slabs."""
         self._check(self._lib.girih_gpu_set_topology(self._ctx, _i3(dims), _i3(coords)), "girih_gpu_set_topology")
 
+    # -- halo push over peer memory (include/girih_cuda.h) ---------------------------------------
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(256)
+        self._check(self._lib.girih_gpu_peer_export(self._ctx, buf, 256), "girih_gpu_peer_export")
+        return buf.raw
+
+    def peer_attach(self, which: int, blob: bytes):
+        self._check(self._lib.girih_gpu_peer_attach(self._ctx, which, blob, len(blob)), "girih_gpu_peer_attach")
+
+    def peer_detach(self):
+        self._check(self._lib.girih_gpu_peer_detach(self._ctx), "girih_gpu_peer_detach")
+
     def comm_init(self, uid: bytes):
         self._check(self._lib.girih_gpu_comm_init(self._ctx, uid, len(uid)), "girih_gpu_comm_init")
 

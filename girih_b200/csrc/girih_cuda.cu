@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <mutex>
@@ -105,6 +106,16 @@ struct girih_gpu_ctx {
   void *d_in[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr};
   bool in_pending[2] = {false, false};
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  // halo push (girih_gpu_peer_export / _peer_attach, option "halo_push"): the z neighbours' arrays and flag words
+  // mapped into this process; [0] = lower neighbour, [1] = upper neighbour
+  int *d_flags = nullptr;                 // [0] written by the lower neighbour, [1] by the upper one, [2] = wait timed out
+  void *peer_U[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [neighbour][array]
+  int *peer_flags[2] = {nullptr, nullptr};
+  int peer_nz[2] = {0, 0};
+  bool peer_ipc[2] = {false, false};      // mapped with cudaIpcOpenMemHandle (to be closed)
+  int opt_push = 0;
+  int push_seq = 0;                       // passes signalled so far (the same number on every rank)
+  int push_planes = 0;                    // planes the pass being launched pushes to each neighbour (0 = none)
   cudaEvent_t ev_in_ready = nullptr, ev_in_free = nullptr, ev_out_ready = nullptr, ev_out_free = nullptr;
   char err[512] = "";
 };
@@ -245,6 +256,8 @@ extern "C" void girih_gpu_destroy(girih_gpu_ctx *c) {
     if (ev) cudaEventDestroy(ev);
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+  girih_gpu_peer_detach(c);
+  if (c->d_flags) cudaFree(c->d_flags);
   for (auto &p : c->comm_ev) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
@@ -282,6 +295,7 @@ extern "C" int girih_gpu_set_option(girih_gpu_ctx *c, const char *key, int value
   else if (!strcmp(key, "overlap")) c->opt_overlap = value;
   else if (!strcmp(key, "contract")) c->opt_contract = (value != 0);
   else if (!strcmp(key, "halo_group")) c->opt_halo_group = value;
+  else if (!strcmp(key, "halo_push")) c->opt_push = value;
   else return fail(c, GIRIH_ERR_ARG, "unknown option '%s'", key);
   return GIRIH_OK;
 }
@@ -532,6 +546,113 @@ extern "C" int girih_gpu_sync_transfers(girih_gpu_ctx *c) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Halo push over peer memory: compute and exchange in ONE kernel.  Each rank maps its z neighbours' field arrays
+// (same process: peer access; other process: CUDA IPC) and the fused sweep stores the boundary planes of every
+// pass straight into the neighbours' halo planes over NVLink while it computes (kernels_r1.cuh, R1_PUSH).  What is
+// left of the exchange is ordering: a pass may start when both neighbours have finished the previous one (their
+// stores into my halos are complete, and they no longer read the halos my pass overwrites).  That is one flag
+// word per neighbour in device memory, written by a one-thread kernel behind each pass and awaited by a one-thread
+// kernel in front of the next -- no host synchronisation, no NCCL kernel competing for SMs.
+//   girih_gpu_peer_export   this rank's handles (GIRIH_PEER_BLOB_BYTES), to be passed to both z neighbours
+//   girih_gpu_peer_attach   maps one neighbour (which = 0 lower, 1 upper) from its blob
+//   option "halo_push" = 1  fused passes of slot 1 use it (default tiles; needs both attach calls where a
+//                           neighbour exists, and comm_init for the first and last exchange of a run)
+// ------------------------------------------------------------------------------------------------
+struct PeerBlob {
+  int magic, pid, device, nz;
+  unsigned long long ptr[3];        // dU[0], dU[1], flags (valid inside the exporting process)
+  cudaIpcMemHandle_t h[3];
+};
+static_assert(sizeof(PeerBlob) <= GIRIH_PEER_BLOB_BYTES, "blob size");
+
+__global__ void k_flag_signal(volatile int *dn_slot, volatile int *up_slot, int v) {
+  __threadfence_system();   // the sweep's stores into peer memory are ordered before the flag
+  if (dn_slot) *dn_slot = v;
+  if (up_slot) *up_slot = v;
+}
+__global__ void k_flag_wait(volatile int *flags, int need_dn, int need_up, int v, long long max_cycles) {
+  const long long t0 = clock64();
+  while ((need_dn && flags[0] - v < 0) || (need_up && flags[1] - v < 0)) {
+    if (clock64() - t0 > max_cycles) { flags[2] = 1; break; }   // a neighbour is gone: give up, the host reports it
+  }
+  __threadfence_system();
+}
+
+extern "C" int girih_gpu_peer_export(girih_gpu_ctx *c, void *blob, size_t len) {
+  if (!c || !blob || len < GIRIH_PEER_BLOB_BYTES) return GIRIH_ERR_ARG;
+  CU(cudaSetDevice(c->device));
+  if (!c->d_flags) {
+    CU(cudaMalloc(&c->d_flags, 4 * sizeof(int)));
+    CU(cudaMemset(c->d_flags, 0, 4 * sizeof(int)));
+  }
+  PeerBlob b;
+  memset(&b, 0, sizeof(b));
+  b.magic = 0x47504252; b.pid = (int)getpid(); b.device = c->device; b.nz = c->g.nz;
+  void *ptrs[3] = {c->dU[0], c->dU[1], c->d_flags};
+  for (int i = 0; i < 3; ++i) {
+    b.ptr[i] = (unsigned long long)(uintptr_t)ptrs[i];
+    CU(cudaIpcGetMemHandle(&b.h[i], ptrs[i]));
+  }
+  memset(blob, 0, len);
+  memcpy(blob, &b, sizeof(b));
+  return GIRIH_OK;
+}
+
+extern "C" int girih_gpu_peer_attach(girih_gpu_ctx *c, int which, const void *blob, size_t len) {
+  if (!c || !blob || len < sizeof(PeerBlob) || which < 0 || which > 1) return GIRIH_ERR_ARG;
+  PeerBlob b;
+  memcpy(&b, blob, sizeof(b));
+  if (b.magic != 0x47504252) return fail(c, GIRIH_ERR_ARG, "not a peer blob");
+  CU(cudaSetDevice(c->device));
+  void *ptrs[3] = {nullptr, nullptr, nullptr};
+  if (b.pid == (int)getpid()) {   // rank threads of one process: the pointers are valid here, the devices need peer access
+    if (b.device != c->device) {
+      int can = 0;
+      CU(cudaDeviceCanAccessPeer(&can, c->device, b.device));
+      if (!can) return fail(c, GIRIH_ERR_UNSUPPORTED, "device %d cannot access device %d", c->device, b.device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+      (void)cudaGetLastError();
+    }
+    for (int i = 0; i < 3; ++i) ptrs[i] = (void *)(uintptr_t)b.ptr[i];
+  } else {
+    for (int i = 0; i < 3; ++i) CU(cudaIpcOpenMemHandle(&ptrs[i], b.h[i], cudaIpcMemLazyEnablePeerAccess));
+    c->peer_ipc[which] = true;
+  }
+  c->peer_U[which][0] = ptrs[0];
+  c->peer_U[which][1] = ptrs[1];
+  c->peer_flags[which] = (int *)ptrs[2];
+  c->peer_nz[which] = b.nz;
+  return GIRIH_OK;
+}
+
+// Unmaps the neighbours (IPC handles are closed).  Importers should detach before an exporter is destroyed: call this
+// on every rank, synchronise the ranks, then destroy.  girih_gpu_destroy calls it as well.
+extern "C" int girih_gpu_peer_detach(girih_gpu_ctx *c) {
+  if (!c) return GIRIH_ERR_ARG;
+  cudaSetDevice(c->device);
+  if (c->s_comp) cudaStreamSynchronize(c->s_comp);
+  for (int n = 0; n < 2; ++n) {
+    if (c->peer_ipc[n]) {
+      for (int a = 0; a < 2; ++a) if (c->peer_U[n][a]) cudaIpcCloseMemHandle(c->peer_U[n][a]);
+      if (c->peer_flags[n]) cudaIpcCloseMemHandle(c->peer_flags[n]);
+    }
+    c->peer_ipc[n] = false;
+    c->peer_U[n][0] = c->peer_U[n][1] = nullptr;
+    c->peer_flags[n] = nullptr;
+  }
+  return GIRIH_OK;
+}
+
+// may this run push its halos?  Same answer on every rank: options and topology are set alike by the host
+static bool push_enabled(const girih_gpu_ctx *c, int Tmax) {
+  if (!c->opt_push || c->nranks == 1 || xy_decomposed(c) || c->kernel != 1 || c->opt_variant == 1 || c->opt_tile != 0) return false;
+  if (Tmax * c->g.r > c->nz_min) return false;
+  const bool need_dn = neighbour(c, 2, -1) >= 0, need_up = neighbour(c, 2, +1) >= 0;
+  return c->d_flags && (!need_dn || c->peer_flags[0]) && (!need_up || c->peer_flags[1]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // NCCL bootstrap and halo exchange
 // ------------------------------------------------------------------------------------------------
 extern "C" int girih_gpu_comm_unique_id(void *id, size_t len) {
@@ -779,6 +900,17 @@ static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb
   sl.variant = c->opt_variant;
   sl.contract = c->opt_contract;
   sl.stream = c->s_comp;
+  if (c->push_planes > 0) {   // this pass also stores its boundary planes into the neighbours' halos (run_passes)
+    const size_t plane_b = (size_t)g.pxy * c->es;
+    if (c->peer_U[1][dst]) {   // my planes [Z0+nz-D, Z0+nz) -> upper neighbour's planes [Z0-D, Z0): shift by -nz
+      sl.push_up = (char *)c->peer_U[1][dst] - (size_t)g.nz * plane_b;
+      sl.push_up_from = g.Z0 + g.nz - c->push_planes;
+    }
+    if (c->peer_U[0][dst]) {   // my planes [Z0, Z0+D) -> lower neighbour's planes [Z0+nz', Z0+nz'+D): shift by +nz'
+      sl.push_dn = (char *)c->peer_U[0][dst] + (size_t)c->peer_nz[0] * plane_b;
+      sl.push_dn_below = g.Z0 + c->push_planes;
+    }
+  }
   c->n_kernels++;
   if (c->kernel == 7) return T == 1 ? launch_box(c->es, sl) : cudaErrorInvalidValue;
   if (g.r == 1) return launch_r1(c->kernel, c->es, T, sl);
@@ -817,6 +949,11 @@ static int end_run(girih_gpu_ctx *c) {
   CU(cudaEventRecord(c->ev_t1, c->s_comp));
   CU(cudaStreamSynchronize(c->s_comp));
   CU(cudaStreamSynchronize(c->s_comm));
+  if (c->d_flags && c->opt_push) {   // did a halo-push wait give up on a neighbour?
+    int gave_up = 0;
+    CU(cudaMemcpy(&gave_up, c->d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost));
+    if (gave_up) return fail(c, GIRIH_ERR_STATE, "halo push: a neighbour did not signal within the time limit");
+  }
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
   c->ms_total = ms;
@@ -891,7 +1028,8 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
   int Tmax = 1;
   for (int s : sizes) Tmax = std::max(Tmax, s);
   if (xy_decomposed(c)) overlap = false;   // x/y faces are exchanged between whole steps only
-  const int group = halo_group(c, Tmax, overlap);
+  const bool push = !overlap && push_enabled(c, Tmax);   // halo push: the sweep itself feeds the neighbours' halos
+  const int group = push ? 1 : halo_group(c, Tmax, overlap);
   std::vector<int> depth;
   plan_exchanges(sizes, r, c->halo_max, group, depth);
   if (group > 1) {
@@ -903,6 +1041,40 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
   for (size_t p = 0; p < sizes.size(); ++p) {
     const int T = sizes[p];
     const int src = cur, dst = cur ^ 1;
+    if (push) {
+      const bool need_dn = neighbour(c, 2, -1) >= 0, need_up = neighbour(c, 2, +1) >= 0;
+      auto signal = [&]() -> cudaError_t {   // "everything I issued so far on the compute stream is done"
+        c->push_seq++;
+        c->n_kernels++;
+        GIRIH_LAUNCH(k_flag_signal, 1, 1, 0, c->s_comp, (volatile int *)(need_dn ? c->peer_flags[0] + 1 : nullptr),
+                     (volatile int *)(need_up ? c->peer_flags[1] + 0 : nullptr), c->push_seq);
+        return cudaGetLastError();
+      };
+      if (p == 0) {
+        // Level-0 halos come through NCCL once per run -- both arrays, because the Dirichlet frame cells of the halo
+        // planes are never pushed (a sweep stores interior points only).  The flag behind the exchange tells the
+        // neighbours that my receives have landed, so none of their pushes can be overtaken by a late receive.
+        if ((rc = timed_exchange(c, c->dU[dst], Tmax * r))) return rc;
+        if ((rc = timed_exchange(c, c->dU[src], T * r))) return rc;
+        CU(signal());
+      }
+      // both neighbours have passed their last signal (end of pass p-1, or of the initial exchange): their stores
+      // into my halos are complete and they no longer read the halo planes this pass overwrites
+      GIRIH_LAUNCH(k_flag_wait, 1, 1, 0, c->s_comp, (volatile int *)c->d_flags, (int)need_dn, (int)need_up, c->push_seq,
+                   20000000000LL);
+      CU(cudaGetLastError());
+      c->n_kernels++;
+      c->push_planes = (p + 1 < sizes.size()) ? sizes[p + 1] * r : 0;   // what the next pass reads beyond its slab
+      cudaError_t le = launch_pass(c, T, src, dst, zb, ze);
+      c->push_planes = 0;
+      CU(le);
+      CU(signal());
+      ready = 0;
+      cur = dst;
+      c->n_passes++;
+      c->n_steps += T;
+      continue;
+    }
     if (c->nranks > 1 && !overlap) {
       if (depth[p] > 0) {
         if ((rc = timed_exchange(c, c->dU[src], depth[p]))) return rc;

@@ -28,6 +28,10 @@ static cudaError_t launch_r1_t(const StreamLaunch &s) {
   a.cc = make_cc<R>(s.cc);
   a.zb0 = s.zb0;
   a.ze0 = s.ze0;
+  a.push_up = (R *)s.push_up;
+  a.push_dn = (R *)s.push_dn;
+  a.push_up_from = s.push_up ? s.push_up_from : 0x7fffffff;
+  a.push_dn_below = s.push_dn ? s.push_dn_below : -0x7fffffff;
   const int ntx = (g.nx + Cfg::UX - 1) / Cfg::UX, nty = (g.ny + Cfg::UY - 1) / Cfg::UY;
   auto kfn = k_r1<K, R, T, PY, NW, DBG>;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
@@ -67,6 +71,12 @@ static cudaError_t launch_r1_t(const StreamLaunch &s) {
 // tile shapes instantiated per (operator, precision, depth); "tile" option = PY*100 + NW
 template <int K, typename R, int T>
 static cudaError_t launch_r1_tile(const StreamLaunch &s) {
+  if constexpr (K == 1) {   // halo push: default tile of slot 1 only (girih_cuda.cu requests it for nothing else)
+    if (s.push_up != nullptr || s.push_dn != nullptr) {
+      if constexpr (sizeof(R) == 8) return s.contract ? launch_r1_t<K, R, T, 4, 8, R1_FM | R1_PUSH>(s) : launch_r1_t<K, R, T, 4, 8, R1_PUSH>(s);
+      else return s.contract ? launch_r1_t<K, R, T, 2, 16, R1_FM | R1_PUSH>(s) : launch_r1_t<K, R, T, 2, 16, R1_PUSH>(s);
+    }
+  }
   if (s.contract) {   // contracted arithmetic: the default tile of each (operator, precision) only
     if constexpr (K == 1) {
       if (s.tile == 5408) return launch_r1_t<K, R, T, 4, 8, R1_FM | R1_SPLIT>(s);

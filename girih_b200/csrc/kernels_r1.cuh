@@ -38,6 +38,12 @@ template <typename R> struct R1Args {
   int zchunk;                   // output planes per CTA
   int nch0;                     // z chunks (blockIdx.z) that belong to [zb0, ze0); the rest cover a second
   int zb1, ze1;                 // range [zb1, ze1): one launch can sweep the two outer parts of a slab
+  // Halo push (R1_PUSH kernels): the output planes the z neighbours read as their halo in the next pass are
+  // also stored straight into the neighbours' arrays over NVLink (peer memory), so a fused pass needs no
+  // separate exchange.  push_up / push_dn point at the neighbour's output array, shifted so that indexing
+  // them with MY plane number lands in its halo; planes >= push_up_from go up, planes < push_dn_below go down.
+  R *push_up, *push_dn;
+  int push_up_from, push_dn_below;
 };
 
 template <typename R, int T, int PY, int NW> struct R1Cfg {
@@ -71,6 +77,7 @@ template <typename R> struct RegNb1 {
 constexpr int R1_FM = 32;   // DBG flag bit: evaluate with the reference's gcc -mfma contraction
 constexpr int R1_SPLIT = 64;   // DBG flag bit: split (arrive ... wait) CTA barrier instead of __syncthreads
 constexpr int R1_REV = 128;    // DBG flag bit: decoupled levels (T > 1), see the comment in k_r1
+constexpr int R1_PUSH = 256;   // DBG flag bit: boundary output planes are also stored into the z neighbours' halos
 
 // Split CTA barrier on an mbarrier in shared memory: a warp ARRIVES as soon as it has published its edge rows
 // and read its neighbours' (before the arithmetic of the last fused level and the global stores) and WAITS at
@@ -379,6 +386,29 @@ k_r1(const R1Args<R> a) {
 #pragma unroll
           for (int e = 0; e < VX; ++e)
             if ((m >> e) & 1u) q[(long long)j * g.px + e] = Ofin[j][e];
+        }
+      }
+    }
+    // halo push: the same rows once more, into the upper / lower neighbour's halo planes (peer memory).  Only the
+    // few iterations that produce boundary planes enter (warp-uniform test on the plane number).
+    if constexpr ((DBG & R1_PUSH) != 0) {
+      if (zst && (zo >= a.push_up_from || zo < a.push_dn_below)) {
+        R *const dsts[2] = {zo >= a.push_up_from ? a.push_up : nullptr, zo < a.push_dn_below ? a.push_dn : nullptr};
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          if (dsts[d] == nullptr) continue;
+          R *qp = dsts[d] + (long long)zo * g.pxy + row0;
+#pragma unroll
+          for (int j = 0; j < PY; ++j) {
+            if ((full_rows >> j) & 1u) {
+              st128<R>(qp + (long long)j * g.px, Ofin[j]);
+            } else if ((part_rows >> j) & 1u) {
+              const unsigned m = (core_xy >> (j * VX)) & ((1u << VX) - 1u);
+#pragma unroll
+              for (int e = 0; e < VX; ++e)
+                if ((m >> e) & 1u) qp[(long long)j * g.px + e] = Ofin[j][e];
+            }
+          }
         }
       }
     }

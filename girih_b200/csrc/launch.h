@@ -28,6 +28,10 @@ struct StreamLaunch {
   int tile;              // 0 = default, else PY*100 + NW
   int variant;           // 0 = auto, 2 = force the fused-sweep kernel also for T = 1
   int contract;          // 1 = FMA-contracted arithmetic (stencil_expr.cuh, Sop<R, true>); default tiles only
+  // halo push (fused r = 1 sweep of slot 1 only): neighbours' output arrays in peer memory, pre-shifted (see R1Args);
+  // nullptr / empty plane ranges when the pass pushes nothing
+  void *push_up = nullptr, *push_dn = nullptr;
+  int push_up_from = 0x7fffffff, push_dn_below = -0x7fffffff;
   cudaStream_t stream;
 };
 

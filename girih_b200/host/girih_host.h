@@ -62,6 +62,7 @@ typedef struct Parameters {
   int gpu_tfuse;                    /* --gpu-tfuse: fused steps per HBM pass for ts 2 (0 = auto) */
   int gpu_variant;                  /* --gpu-variant: 0 auto, 1 naive kernels */
   int gpu_overlap;                  /* --gpu-overlap: overlap halo exchange with compute */
+  int gpu_push;                     /* --gpu-push: fused passes store boundary planes into the neighbours' halos (peer memory) */
   int gpu_tune;                     /* --gpu-tune: on-device search over fusion depth and tiles ([AUTO TUNE]) */
   int gpu_contract;                 /* --gpu-contract: FMA-contracted arithmetic (reference built with -mfma) */
   /* decomposition */
@@ -125,6 +126,7 @@ void team_init(int nranks);
 void team_barrier(void);
 void team_reduce(const double *in, double *max, double *min, double *sum, int n, int rank);
 void team_bcast(void *buf, size_t len, int root, int rank);
+void team_allgather(const void *mine, size_t len, void *all, int rank);   /* all: nranks * len bytes, len <= 256 */
 void *team_shared_alloc(size_t bytes, int rank);     /* collective: same pointer on every rank */
 void team_shared_free(void *ptr, int rank);
 void team_run(int nranks, void (*fn)(int rank, void *arg), void *arg);

@@ -13,7 +13,7 @@ HOST_LIBS = {4: os.path.join(PKG, "libgirih_host_sp.so"), 8: os.path.join(PKG, "
 # every symbol include/girih_cuda.h declares
 ABI_SYMBOLS = [
     "girih_kernel_count", "girih_kernel_info", "girih_gpu_count", "girih_gpu_create", "girih_gpu_destroy",
-    "girih_gpu_comm_unique_id", "girih_gpu_comm_init", "girih_gpu_set_topology", "girih_gpu_upload", "girih_gpu_download",
+    "girih_gpu_comm_unique_id", "girih_gpu_comm_init", "girih_gpu_set_topology", "girih_gpu_peer_export", "girih_gpu_peer_attach", "girih_gpu_peer_detach", "girih_gpu_upload", "girih_gpu_download",
     "girih_gpu_upload_fields", "girih_gpu_prefetch_fields", "girih_gpu_commit_fields", "girih_gpu_download_async",
     "girih_gpu_sync_transfers", "girih_gpu_run_single", "girih_gpu_run_fused", "girih_gpu_step_box",
     "girih_gpu_time_pass", "girih_gpu_last_elapsed_ms", "girih_gpu_last_launch_info", "girih_gpu_scan_u1", "girih_gpu_set_option",
@@ -54,6 +54,9 @@ def declare(lib: C.CDLL) -> C.CDLL:
     lib.girih_gpu_comm_unique_id.argtypes = [P, C.c_size_t]
     lib.girih_gpu_comm_init.argtypes = [P, P, C.c_size_t]
     lib.girih_gpu_set_topology.argtypes = [P, C.POINTER(I), C.POINTER(I)]
+    lib.girih_gpu_peer_export.argtypes = [P, P, C.c_size_t]
+    lib.girih_gpu_peer_attach.argtypes = [P, I, P, C.c_size_t]
+    lib.girih_gpu_peer_detach.argtypes = [P]
     lib.girih_gpu_upload.argtypes = [P, P, P, P, P]
     lib.girih_gpu_download.argtypes = [P, P, P]
     lib.girih_gpu_upload_fields.argtypes = [P, P, P]

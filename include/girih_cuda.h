@@ -104,6 +104,21 @@ void girih_gpu_destroy(girih_gpu_ctx *ctx);
 int girih_gpu_comm_unique_id(void *id, size_t len);
 int girih_gpu_comm_init(girih_gpu_ctx *ctx, const void *id, size_t len);
 
+/* Halo push: compute and z exchange in one kernel over NVLink peer memory (no reference counterpart; the GPU form of
+ * the reference's compute/communication overlap, src/kernels/halo_first_ts.c:156-194).  Every rank exports handles of
+ * its field arrays and of a flag word (girih_gpu_peer_export, GIRIH_PEER_BLOB_BYTES), the host hands each blob to the
+ * rank's two z neighbours, which map it (girih_gpu_peer_attach: which = 0 for the blob of the lower neighbour, 1 for
+ * the upper one; rank threads of one process use peer access, separate processes CUDA IPC).  With
+ * girih_gpu_set_option("halo_push", 1) the fused passes of slot 1 then store their boundary planes straight into the
+ * neighbours' halo planes while they sweep; a pass starts when both neighbours have flagged the end of the previous
+ * one (device-side flags, no host synchronisation, no NCCL kernel between passes).  NCCL still carries the first and
+ * the last exchange of a run.  Every rank must make the same calls. */
+#define GIRIH_PEER_BLOB_BYTES 256
+int girih_gpu_peer_export(girih_gpu_ctx *ctx, void *blob, size_t len);
+int girih_gpu_peer_attach(girih_gpu_ctx *ctx, int which, const void *blob, size_t len);
+/* unmaps both neighbours; between processes: detach on every rank, synchronise the ranks, then destroy */
+int girih_gpu_peer_detach(girih_gpu_ctx *ctx);
+
 /* Process topology (--npx/--npy/--npz; MPI_Cart_create / MPI_Cart_coords / MPI_Cart_shift of
  * src/mpi_utils.c:63-81): dims = (npx, npy, npz) with npx*npy*npz == nranks, coords = this rank's position,
  * rank == (coords[0]*npy + coords[1])*npz + coords[2] (MPI's row-major order).  Optional -- without it the ranks

@@ -252,7 +252,8 @@ void launch_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()>
     last_error = cudaErrorInvalidValue;   // what cudaGetLastError() reports for an invalid configuration
     return;
   }
-  if (nthr % 32 != 0) { last_error = cudaErrorInvalidValue; return; }   // the emulator models whole warps only
+  // a partial last warp is accepted, but its threads must not take part in warp collectives (none of the
+  // kernels launched that way -- one-thread flag kernels -- do)
   const char *e = getenv("CUDA_EMU_SCHED");
   g_sched = e ? atoi(e) : 0;
   const long nblocks = (long)grid.x * grid.y * grid.z;

@@ -78,6 +78,7 @@ test_xy_topologies_match_global_oracle = P.test_xy_topologies_match_global_oracl
 test_autotune_then_results_are_unchanged = P.test_autotune_then_results_are_unchanged
 test_overlap_with_uneven_slabs_takes_one_schedule_on_every_rank = P.test_overlap_with_uneven_slabs_takes_one_schedule_on_every_rank
 test_pipelined_transfers_keep_jobs_apart = P.test_pipelined_transfers_keep_jobs_apart
+test_halo_push_matches_global_oracle = P.test_halo_push_matches_global_oracle
 test_cli_verify = P.test_cli_verify
 test_cli_verify_contracted = P.test_cli_verify_contracted
 test_cli_autotune_prints_reference_prefix = P.test_cli_autotune_prints_reference_prefix
@@ -185,3 +186,12 @@ def test_cli_diamond_rejects_xy_topologies():
     rc, out, err = emu_cli(np.float64, ["--nx", 48, "--ny", 32, "--nz", 40, "--nt", 20, "--target-ts", 2, "--target-kernel", 1,
                                         "--t-dim", 3, "--verify", 1, "--npx", 2])
     assert rc == 1 and "ERROR: the Diamond stepper of this build decomposes the domain across the Z direction only" in err
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_cli_halo_push(dt):
+    """mwd_kernel --npz 3 --gpu-push 1: rank threads map each other's arrays, the Diamond stepper pushes its halos"""
+    rc, out, err = emu_cli(dt, ["--nx", 70, "--ny", 32, "--nz", 50, "--nt", 30, "--target-ts", 2, "--target-kernel", 1,
+                                "--t-dim", 3, "--verify", 1, "--npz", 3, "--gpu-push", 1, "--verbose", 0])
+    assert rc == 0, out + err
+    assert "eMax:0.000e+00|eL1:0.000e+00-PASSED" in out
