@@ -116,6 +116,27 @@ template <int N, typename F> __device__ __forceinline__ void static_for_rev(F &&
   }
 }
 
+// halo push: one thread's rows of an output plane once more, into a neighbour's halo plane (peer memory).  A
+// force-inlined function, not a lambda: a call the inliner declines would put the kernel on the ABI path (stack frame,
+// 71 registers).
+template <typename R, int PY, int VX>
+__device__ __forceinline__ void push_rows(R *qp, const R (&O)[PY][VX], unsigned full_rows, unsigned part_rows,
+                                          unsigned core_xy, int px, bool any_part) {
+#pragma unroll
+  for (int j = 0; j < PY; ++j)
+    if ((full_rows >> j) & 1u) st128<R>(qp + (long long)j * px, O[j]);
+  if (any_part) {   // rows cut by the domain edge (nx not a multiple of VX)
+#pragma unroll
+    for (int j = 0; j < PY; ++j) {
+      if ((part_rows >> j) & 1u) {
+#pragma unroll
+        for (int e = 0; e < VX; ++e)
+          if ((core_xy >> (j * VX + e)) & 1u) qp[(long long)j * px + e] = O[j][e];
+      }
+    }
+  }
+}
+
 template <int K, typename R, int T, int PY, int NW, int DBG = 0>
 __global__ void __launch_bounds__(32 * NW, R1Cfg<R, T, PY, NW>::MINB)
 k_r1(const R1Args<R> a) {
@@ -392,25 +413,10 @@ k_r1(const R1Args<R> a) {
     // halo push: the same rows once more, into the upper / lower neighbour's halo planes (peer memory).  Only the
     // few iterations that produce boundary planes enter (warp-uniform test on the plane number).
     if constexpr ((DBG & R1_PUSH) != 0) {
-      if (zst && (zo >= a.push_up_from || zo < a.push_dn_below)) {
-        R *const dsts[2] = {zo >= a.push_up_from ? a.push_up : nullptr, zo < a.push_dn_below ? a.push_dn : nullptr};
-#pragma unroll
-        for (int d = 0; d < 2; ++d) {
-          if (dsts[d] == nullptr) continue;
-          R *qp = dsts[d] + (long long)zo * g.pxy + row0;
-#pragma unroll
-          for (int j = 0; j < PY; ++j) {
-            if ((full_rows >> j) & 1u) {
-              st128<R>(qp + (long long)j * g.px, Ofin[j]);
-            } else if ((part_rows >> j) & 1u) {
-              const unsigned m = (core_xy >> (j * VX)) & ((1u << VX) - 1u);
-#pragma unroll
-              for (int e = 0; e < VX; ++e)
-                if ((m >> e) & 1u) qp[(long long)j * g.px + e] = Ofin[j][e];
-            }
-          }
-        }
-      }
+      if (zst && zo >= a.push_up_from)
+        push_rows<R, PY, VX>(a.push_up + (long long)zo * g.pxy + row0, Ofin, full_rows, part_rows, core_xy, g.px, any_part);
+      if (zst && zo < a.push_dn_below)
+        push_rows<R, PY, VX>(a.push_dn + (long long)zo * g.pxy + row0, Ofin, full_rows, part_rows, core_xy, g.px, any_part);
     }
     if constexpr (!(DBG & 2) && !SPLIT) __syncthreads();
   };
@@ -423,6 +429,17 @@ k_r1(const R1Args<R> a) {
     else if (warp_masked || (zin - LAG * (T - 1) - 1 < g.zlo) || (zin > g.zhi)) body(phase_tag, FrameTag<true>{}, it);
     else body(phase_tag, FrameTag<false>{}, it);
   };
+  if constexpr ((DBG & R1_PUSH) != 0) {
+    // one copy of each phase instead of loop + remainder copies: with the push stores the fully unrolled form
+    // outgrows the inliner's budget in fp32 and the bodies would become real calls (stack frame, 71 registers)
+    for (int it = 0; it < nit;) {
+      step(Phase<0>{}, it++);
+      if (it >= nit) break;
+      step(Phase<1>{}, it++);
+      if (it >= nit) break;
+      step(Phase<2>{}, it++);
+    }
+  } else {
   int it = 0;
   for (; it + 3 <= nit; it += 3) {
     step(Phase<0>{}, it);
@@ -431,6 +448,7 @@ k_r1(const R1Args<R> a) {
   }
   if (it < nit) { step(Phase<0>{}, it); ++it; }
   if (it < nit) { step(Phase<1>{}, it); }
+  }
   }
 }
 
