@@ -10,20 +10,27 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include "girih_host.h"
 
 /* The reference's RAISE_ERROR (src/data_structures.h:299-314): message on stderr, exit(1). */
 void girih_fatal(const Parameters *p, const char *fmt, ...) {
-  if (p == NULL || p->mpi_rank == 0) {
+  /* ranks are host threads of one process (team.c): whichever rank gets here first reports, once, before any
+   * rank can end the process -- waiting for rank 0 would race with another rank's exit() */
+  static int reported = 0;
+  (void)p;
+  if (__sync_lock_test_and_set(&reported, 1) == 0) {
     va_list ap;
     fprintf(stderr, "ERROR: ");
     va_start(ap, fmt);
     vfprintf(stderr, fmt, ap);
     va_end(ap);
     fprintf(stderr, "\n");
+    fflush(stderr);
+    exit(1);
   }
-  exit(1);
+  for (;;) pause(); /* another rank is reporting: let it finish the message and end the process */
 }
 
 static void set_kernels(Parameters *p) { /* src/utils.c:253-262 */
