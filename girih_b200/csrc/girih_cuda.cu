@@ -1285,8 +1285,8 @@ static std::vector<int> tile_candidates(const girih_gpu_ctx *c, int T) {
     return {0, 108, 208, 404, 408};
   }
   // 5xxx = split-barrier variants (profiles/kernel_sweep_r01.md, round 1b: +3..8% at T = 2, 3 and in fp32)
-  if (c->opt_contract) return c->kernel == 1 ? std::vector<int>{0, 5408, 5216} : std::vector<int>{0};
-  if (c->kernel == 1) return {216, 408, 312, 310, 316, 5408, 5216};
+  if (c->opt_contract) return c->kernel == 1 ? std::vector<int>{0, 5408, 5216, 9408, 9216} : std::vector<int>{0};
+  if (c->kernel == 1) return {216, 408, 312, 310, 316, 5408, 5216, 9408, 9216};
   return {216, 408};
 }
 

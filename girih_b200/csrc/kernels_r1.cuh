@@ -78,6 +78,7 @@ constexpr int R1_FM = 32;   // DBG flag bit: evaluate with the reference's gcc -
 constexpr int R1_SPLIT = 64;   // DBG flag bit: split (arrive ... wait) CTA barrier instead of __syncthreads
 constexpr int R1_REV = 128;    // DBG flag bit: decoupled levels (T > 1), see the comment in k_r1
 constexpr int R1_PUSH = 256;   // DBG flag bit: boundary output planes are also stored into the z neighbours' halos
+constexpr int R1_TRAP = 512;   // DBG flag bit: warps outside the rows a level is needed on skip that level (see k_r1)
 
 // Split CTA barrier on an mbarrier in shared memory: a warp ARRIVES as soon as it has published its edge rows
 // and read its neighbours' (before the arithmetic of the last fused level and the global stores) and WAITS at
@@ -155,6 +156,14 @@ k_r1(const R1Args<R> a) {
   constexpr bool REV = (DBG & R1_REV) != 0 && T > 1;
   constexpr int LAG = REV ? 2 : 1;
   static_assert(!(REV && SPLIT), "not combined");
+  // Trapezoid skip (TRAP): the plane the last level produces is only needed on the core rows [T, H-T) of the tile,
+  // so a warp whose PY rows all lie outside the core skips the last level and the stores altogether (warp-uniform
+  // branch around arithmetic + stores: no shuffles, no shared-memory reads, nothing live across it).  Only the
+  // LAST level is skipped: branches around the inner levels split the fused basic block and spill.  With PY = 4,
+  // T = 4 the first and last warp skip 1 of 4 levels (1/16 of the tile's updates), with PY = 2, T = 4 two warps on
+  // each side do (also 1/16).
+  constexpr bool TRAP = (DBG & R1_TRAP) != 0 && T > 1 && PY <= T;
+  static_assert(!(TRAP && (REV || SPLIT)), "not combined");
   constexpr unsigned ALL = (PY * VX >= 32) ? 0xffffffffu : ((1u << (PY * VX)) - 1u);
   static_assert(KTraits<K>::R == 1 && KTraits<K>::TO == 1, "radius-1, first-order-in-time only");
   static_assert(PY * VX <= 32, "point masks are 32 bits");
@@ -205,6 +214,7 @@ k_r1(const R1Args<R> a) {
   }
   // warps that lie completely inside the domain skip the per-point pass-through fix-up
   const bool warp_masked = __any_sync(0xffffffffu, interior_xy != ALL);
+  const bool outer_warp = ((warp + 1) * PY <= T) || (warp * PY >= H - T);   // no core row (TRAP)
   unsigned full_rows = 0, part_rows = 0;   // rows stored whole / rows stored point by point
 #pragma unroll
   for (int j = 0; j < PY; ++j) {
@@ -386,9 +396,7 @@ k_r1(const R1Args<R> a) {
         load_plane(zin + 1, S[0][iB], (it + 1 < nit) && (!REV || zin + 1 < ze + T));
       }
     };
-    if constexpr (REV) static_for_rev<T>(level);
-    else static_for<0, T>(level);
-
+    auto store_out = [&]() {
     // Ofin is level T at plane zin - LAG*(T-1) - 1.  Rows whose VX points all lie in the core go out as predicated
     // 128-bit stores (no branches); rows cut by the domain edge (nx not a multiple of VX) are rare and
     // take a warp-uniform slow path.
@@ -417,6 +425,20 @@ k_r1(const R1Args<R> a) {
         push_rows<R, PY, VX>(a.push_up + (long long)zo * g.pxy + row0, Ofin, full_rows, part_rows, core_xy, g.px, any_part);
       if (zst && zo < a.push_dn_below)
         push_rows<R, PY, VX>(a.push_dn + (long long)zo * g.pxy + row0, Ofin, full_rows, part_rows, core_xy, g.px, any_part);
+    }
+    };
+    if constexpr (REV) {
+      static_for_rev<T>(level);
+      store_out();
+    } else if constexpr (TRAP) {
+      static_for<0, T - 1>(level);
+      if (!outer_warp) {
+        level(Level<T - 1>{});
+        store_out();
+      }
+    } else {
+      static_for<0, T>(level);
+      store_out();
     }
     if constexpr (!(DBG & 2) && !SPLIT) __syncthreads();
   };

@@ -219,7 +219,10 @@ int girih_gpu_scan_u1(girih_gpu_ctx *ctx, uint64_t *n_nan_inf, uint64_t *n_zero)
  *   "variant"  0 auto (marching kernel for single steps, fused sweep for T > 1), 1 naive kernels,
  *              2 fused-sweep kernel also for T = 1
  *   "zchunk"   output planes per CTA (0 = choose)
- *   "tile"     fused sweep: PY*100 + NW (rows per thread, warps per CTA); marching kernel: rows per CTA
+ *   "tile"     fused sweep: PY*100 + NW (rows per thread, warps per CTA); marching kernel: rows per CTA.
+ *              Slot 1 also has schedule variants of the tiles 408 and 216, all bit-identical in their results:
+ *              5000 + tile split (arrive/wait) CTA barrier, 7000 + tile decoupled levels, 9000 + tile trapezoid
+ *              skip (warps without a core row skip the last fused level)
  *   "overlap"  fused passes: compute the slab boundaries first and overlap the deep-halo exchange with
  *              the interior (default 0: one exchange per pass, ordered before it, measured faster)
  *   "halo_group" z-slab runs of first-order-in-time operators: fused passes served by one halo exchange
@@ -229,7 +232,8 @@ int girih_gpu_scan_u1(girih_gpu_ctx *ctx, uint64_t *n_nan_inf, uint64_t *n_zero)
  *              and to its -O0 verifier (src/verification.c).  1: the fused multiply-adds gcc emits for the
  *              same FUNC_BODY under `-O3 -mfma` (first product fused onto the second, later products
  *              onto the running sum) -- bit-identical to the reference built that way; 30 % fewer FP64
- *              instructions per lattice update.  With 1 the "tile" option is ignored (default tiles). */
+ *              instructions per lattice update.  With 1 only the default tile and slot 1's schedule variants
+ *              (5xxx, 7xxx, 9xxx) exist; any other "tile" runs the default tile. */
 int girih_gpu_set_option(girih_gpu_ctx *ctx, const char *key, int value);
 
 /* On-device tuner -- the GPU analogue of auto_tune_params() (src/kernels/diamond_utils.c:691-847, the

@@ -18,7 +18,7 @@ import girih_b200 as G  # noqa: E402
 from girih_b200 import lib as L  # noqa: E402
 from oracle import girih_oracle as O  # noqa: E402
 
-TILES_F = {1: (0, 216, 408, 312, 310, 316, 5408, 5216, 7408, 7216), 2: (0, 216, 408), 3: (0, 216, 408), 5: (0, 216, 408)}
+TILES_F = {1: (0, 216, 408, 312, 310, 316, 5408, 5216, 7408, 7216, 9408, 9216), 2: (0, 216, 408), 3: (0, 216, 408), 5: (0, 216, 408)}
 TILES_S = {0: (0, 8, 16, 116), 4: (0, 8, 16), 7: (0, 4), 1: (0, 108, 208, 404, 408), 2: (0, 108, 208, 404, 408),
            3: (0, 108, 208, 404, 408), 5: (0, 108, 208, 404, 408)}
 
@@ -38,7 +38,7 @@ def fuzz_kernels(seed, seconds, max_cases=10 ** 9, log=print):
         if fused:
             T = rnd.randint(1, d.max_tfuse)
             tile, variant = rnd.choice(TILES_F[k]), 2
-            if contract and tile not in (0, 5408, 5216, 7408, 7216):
+            if contract and tile not in (0, 5408, 5216, 7408, 7216, 9408, 9216):
                 tile = 0
             nsteps = rnd.randint(1, 3 * T + 2)
             sizes = G.plan_fused_passes(nsteps, T)

@@ -96,7 +96,7 @@ def test_single_step_kernels_contracted(oracle, kernel, dt):
 # ------------------------------------------------------------------------------------------------
 # fused sweep k_r1: every depth and tile shape the launcher offers
 # ------------------------------------------------------------------------------------------------
-FUSED_TILES = {1: (0, 216, 408, 312, 310, 316, 5408, 5216, 7408, 7216), 2: (0, 216, 408), 3: (0, 216, 408), 5: (0, 216, 408)}
+FUSED_TILES = {1: (0, 216, 408, 312, 310, 316, 5408, 5216, 7408, 7216, 9408, 9216), 2: (0, 216, 408), 3: (0, 216, 408), 5: (0, 216, 408)}
 
 
 @pytest.mark.parametrize("dt", [F32, F64], ids=["sp", "dp"])
@@ -156,6 +156,8 @@ def test_schedule_order_independence(oracle, monkeypatch, order):
              (1, F64, [2, 2, 1], dict(variant=2, tile=5408, zchunk=6, contract=True)),
              (1, F64, [4, 4, 1], dict(variant=2, tile=7408)), (1, F32, [3, 3, 1], dict(variant=2, tile=7216, zchunk=5)),
              (1, F64, [2, 2, 1], dict(variant=2, tile=7408, contract=True)),
+             (1, F64, [4, 4, 1], dict(variant=2, tile=9408)), (1, F32, [4, 4, 1], dict(variant=2, tile=9216, zchunk=5)),
+             (1, F64, [4, 2, 1], dict(variant=2, tile=9216, contract=True)),
              (2, F64, [3, 3, 1], dict(variant=2)), (5, F32, [2, 2, 1], dict(variant=2)),
              (0, F64, [1, 1], {}), (0, F32, [1, 1], dict(tile=16)), (0, F32, [1, 1], dict(tile=116)),
              (4, F64, [1, 1], {}), (4, F32, [1, 1], dict(tile=8)), (7, F64, [1, 1], {}), (1, F64, [1, 1], {})]

@@ -207,6 +207,29 @@ def test_tiles_and_z_chunks(oracle, tile, zchunk):
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("tile", [5408, 5216, 9408, 9216])
+def test_schedule_variant_tiles(oracle, tile, dt):
+    """opt-in schedules of the fused sweep (the tuner's extra candidates): split barrier (5xxx) and trapezoid
+    skip (9xxx, outer warps skip the last fused level) are bit-identical to the default kernel's results, in
+    both arithmetic modes"""
+    st, nsteps = (150, 71, 23), 9
+    for contract in (0, 1):
+        ob = oracle.make_problem(1, st, dt)
+        oracle.run_steps(ob, nsteps, contract=bool(contract))
+        for tf, zchunk in ((4, 0), (3, 6), (2, 0)):
+            pb = G.make_problem(1, st, dt)
+            s = G.GpuStepper.for_problem(pb)
+            s.set_option("variant", 2)
+            s.set_option("tile", tile)
+            s.set_option("zchunk", zchunk)
+            s.set_option("contract", contract)
+            s.run_fused(nsteps, tf)
+            s.download(pb.U1, pb.U2)
+            s.close()
+            assert_same(pb, ob)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("kernel", [1, 2, 3, 5])
 def test_marching_kernel_tiles(oracle, kernel, dt):
     """single-step marching kernel: rows per CTA x z chunking x ragged sizes spanning several tiles"""

@@ -16,7 +16,7 @@ python bench.py --e2e-mode pipelined --no-cpu-baseline > gpurun_out/r2_bench_e2e
 kill $SMI
 # default tiles vs split barrier (5xxx) vs decoupled levels (7xxx), then every tile through the sweep tool
 python tools/split_bench.py > gpurun_out/r2_sweep_schedules.log 2>&1
-python tools/kbench.py --kernels 1 --dtypes f64,f32 --tfuse 2,3,4 --tiles 0,216,408,312,5408,5216 --variants 2 \
+python tools/kbench.py --kernels 1 --dtypes f64,f32 --tfuse 2,3,4 --tiles 0,216,408,312,5408,5216,9408,9216 --variants 2 \
   > gpurun_out/r2_kbench_k1.log 2>&1
 python tools/kbench.py --kernels 0,2,3,4,5,7 --dtypes f64,f32 --tfuse 1,2,3 > gpurun_out/r2_kbench_others.log 2>&1
 # profiler passes: never a bench value

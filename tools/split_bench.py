@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Round-1b experiments on the fused sweep: split (arrive/wait) CTA barrier (tiles 5xxx) and decoupled
-levels (tiles 7xxx) vs the default kernel.
+"""Round-1b experiments on the fused sweep: split (arrive/wait) CTA barrier (tiles 5xxx), decoupled
+levels (tiles 7xxx) and the trapezoid skip (tiles 9xxx) vs the default kernel.
 Checks bit-equality of the variants on a ragged grid, then times one pass at 512^3 (fp64 and fp32,
 strict and contracted arithmetic).  Measurement tool, not part of the product path."""
 import os
@@ -15,7 +15,7 @@ import girih_b200 as G  # noqa: E402
 
 
 def parity():
-    for dt, tiles in ((np.float64, (0, 5408, 5216, 7408, 7216)), (np.float32, (0, 5216, 5408, 7216, 7408))):
+    for dt, tiles in ((np.float64, (0, 5408, 5216, 7408, 7216, 9408, 9216)), (np.float32, (0, 5216, 5408, 7216, 7408, 9216, 9408))):
         ref = None
         for tile in tiles:
             for contract in (0, 1):
@@ -36,7 +36,7 @@ def parity():
 
 
 def bench(n=512):
-    for dt, tiles in ((np.float64, (0, 5408, 7408)), (np.float32, (0, 5216, 7216))):
+    for dt, tiles in ((np.float64, (0, 5408, 7408, 9408, 9216)), (np.float32, (0, 5216, 7216, 9216, 9408))):
         t0 = time.time()
         pb = G.make_problem(1, (n, n, n), dt)
         s = G.GpuStepper.for_problem(pb)
