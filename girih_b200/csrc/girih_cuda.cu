@@ -1287,7 +1287,7 @@ static std::vector<int> tile_candidates(const girih_gpu_ctx *c, int T) {
   // 5xxx = split-barrier variants (profiles/kernel_sweep_r01.md, round 1b: +3..8% at T = 2, 3 and in fp32)
   if (c->opt_contract) return c->kernel == 1 ? std::vector<int>{0, 5408, 5216, 9408, 9216} : std::vector<int>{0};
   if (c->kernel == 1) return {216, 408, 312, 310, 316, 5408, 5216, 9408, 9216};
-  return {216, 408};
+  return {216, 408, 9216, 9408};
 }
 
 extern "C" int girih_gpu_autotune(girih_gpu_ctx *c, int fused, int verbose, int *best_tfuse, int *best_tile,

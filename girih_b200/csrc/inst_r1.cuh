@@ -83,8 +83,8 @@ static cudaError_t launch_r1_tile(const StreamLaunch &s) {
       if (s.tile == 5216) return launch_r1_t<K, R, T, 2, 16, R1_FM | R1_SPLIT>(s);
       if (s.tile == 7408) return launch_r1_t<K, R, T, 4, 8, R1_FM | R1_REV>(s);
       if (s.tile == 7216) return launch_r1_t<K, R, T, 2, 16, R1_FM | R1_REV>(s);
-      if (s.tile == 9408) return launch_r1_t<K, R, T, 4, 8, R1_FM | R1_TRAP>(s);
-      if (s.tile == 9216) return launch_r1_t<K, R, T, 2, 16, R1_FM | R1_TRAP>(s);
+      if (s.tile == 9408) return launch_r1_t<K, R, T, 4, 8, R1_FM | (T >= 4 ? R1_TRAP : 0)>(s);
+      if (s.tile == 9216) return launch_r1_t<K, R, T, 2, 16, R1_FM | (T >= 2 ? R1_TRAP : 0)>(s);
     }
     if constexpr (KTraits<K>::NCA == 0 && sizeof(R) == 8) return launch_r1_t<K, R, T, 4, 8, R1_FM>(s);
     else return launch_r1_t<K, R, T, 2, 16, R1_FM>(s);
@@ -106,6 +106,11 @@ static cudaError_t launch_r1_tile(const StreamLaunch &s) {
     if (s.tile == 2216) return launch_r1_t<K, R, T, 2, 16, 2>(s);
   }
 #endif
+  // trapezoid skip (kernels_r1.cuh, TRAP): 9000 + tile, every radius-1 operator (the per-point coefficient loads of
+  // the skipped level go as well).  A warp can only lie outside the core when PY <= T: below that depth the tile is
+  // the plain one (same instantiation, no second copy of the kernel)
+  if (s.tile == 9408) return launch_r1_t<K, R, T, 4, 8, (T >= 4 ? R1_TRAP : 0)>(s);
+  if (s.tile == 9216) return launch_r1_t<K, R, T, 2, 16, (T >= 2 ? R1_TRAP : 0)>(s);
   if constexpr (K == 1) {
     // split-barrier variants: 5000 + tile
     if (s.tile == 5408) return launch_r1_t<K, R, T, 4, 8, R1_SPLIT>(s);
@@ -113,9 +118,6 @@ static cudaError_t launch_r1_tile(const StreamLaunch &s) {
     // decoupled levels (kernels_r1.cuh, REV): 7000 + tile
     if (s.tile == 7408) return launch_r1_t<K, R, T, 4, 8, R1_REV>(s);
     if (s.tile == 7216) return launch_r1_t<K, R, T, 2, 16, R1_REV>(s);
-    // trapezoid skip (kernels_r1.cuh, TRAP): 9000 + tile
-    if (s.tile == 9408) return launch_r1_t<K, R, T, 4, 8, R1_TRAP>(s);
-    if (s.tile == 9216) return launch_r1_t<K, R, T, 2, 16, R1_TRAP>(s);
     if (s.tile == 312) return launch_r1_t<K, R, T, 3, 12>(s);
     if (s.tile == 310) return launch_r1_t<K, R, T, 3, 10>(s);
     if (s.tile == 316) return launch_r1_t<K, R, T, 3, 16>(s);

@@ -220,9 +220,9 @@ int girih_gpu_scan_u1(girih_gpu_ctx *ctx, uint64_t *n_nan_inf, uint64_t *n_zero)
  *              2 fused-sweep kernel also for T = 1
  *   "zchunk"   output planes per CTA (0 = choose)
  *   "tile"     fused sweep: PY*100 + NW (rows per thread, warps per CTA); marching kernel: rows per CTA.
- *              Slot 1 also has schedule variants of the tiles 408 and 216, all bit-identical in their results:
- *              5000 + tile split (arrive/wait) CTA barrier, 7000 + tile decoupled levels, 9000 + tile trapezoid
- *              skip (warps without a core row skip the last fused level)
+ *              Schedule variants of the tiles 408 and 216, all bit-identical in their results: 9000 + tile
+ *              trapezoid skip (warps without a core row skip the last fused level; slots 1, 2, 3, 5), and for
+ *              slot 1 5000 + tile split (arrive/wait) CTA barrier, 7000 + tile decoupled levels
  *   "overlap"  fused passes: compute the slab boundaries first and overlap the deep-halo exchange with
  *              the interior (default 0: one exchange per pass, ordered before it, measured faster)
  *   "halo_group" z-slab runs of first-order-in-time operators: fused passes served by one halo exchange

@@ -96,7 +96,7 @@ def test_single_step_kernels_contracted(oracle, kernel, dt):
 # ------------------------------------------------------------------------------------------------
 # fused sweep k_r1: every depth and tile shape the launcher offers
 # ------------------------------------------------------------------------------------------------
-FUSED_TILES = {1: (0, 216, 408, 312, 310, 316, 5408, 5216, 7408, 7216, 9408, 9216), 2: (0, 216, 408), 3: (0, 216, 408), 5: (0, 216, 408)}
+FUSED_TILES = {1: (0, 216, 408, 312, 310, 316, 5408, 5216, 7408, 7216, 9408, 9216), 2: (0, 216, 408, 9216, 9408), 3: (0, 216, 408, 9216, 9408), 5: (0, 216, 408, 9216, 9408)}
 
 
 @pytest.mark.parametrize("dt", [F32, F64], ids=["sp", "dp"])

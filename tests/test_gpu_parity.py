@@ -230,6 +230,28 @@ def test_schedule_variant_tiles(oracle, tile, dt):
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("kernel", [2, 3, 5])
+def test_trapezoid_skip_variable_coefficients(oracle, kernel, dt):
+    """trapezoid skip for the per-point-coefficient operators (the skipped level's coefficient loads go too)"""
+    st = (150, 71, 23)
+    tmax = G.kernel_info(kernel).max_tfuse
+    nsteps = 2 * tmax + 1
+    ob = oracle.make_problem(kernel, st, dt)
+    oracle.run_steps(ob, nsteps)
+    for tile in (9216, 9408):
+        for tf, zchunk in ((tmax, 0), (2, 6)):
+            pb = G.make_problem(kernel, st, dt)
+            s = G.GpuStepper.for_problem(pb)
+            s.set_option("variant", 2)
+            s.set_option("tile", tile)
+            s.set_option("zchunk", zchunk)
+            s.run_fused(nsteps, tf)
+            s.download(pb.U1, pb.U2)
+            s.close()
+            assert_same(pb, ob)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("kernel", [1, 2, 3, 5])
 def test_marching_kernel_tiles(oracle, kernel, dt):
     """single-step marching kernel: rows per CTA x z chunking x ragged sizes spanning several tiles"""

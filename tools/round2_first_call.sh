@@ -18,7 +18,8 @@ kill $SMI
 python tools/split_bench.py > gpurun_out/r2_sweep_schedules.log 2>&1
 python tools/kbench.py --kernels 1 --dtypes f64,f32 --tfuse 2,3,4 --tiles 0,216,408,312,5408,5216,9408,9216 --variants 2 \
   > gpurun_out/r2_kbench_k1.log 2>&1
-python tools/kbench.py --kernels 0,2,3,4,5,7 --dtypes f64,f32 --tfuse 1,2,3 > gpurun_out/r2_kbench_others.log 2>&1
+python tools/kbench.py --kernels 0,4,7 --dtypes f64,f32 --tfuse 1 > gpurun_out/r2_kbench_others.log 2>&1
+python tools/kbench.py --kernels 2,3,5 --dtypes f64,f32 --tfuse 1,2,3 --tiles 0,9216 >> gpurun_out/r2_kbench_others.log 2>&1
 # profiler passes: never a bench value
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv \
   python bench.py --steps 2 --warmup 1 > gpurun_out/r2_launches_bench.log 2>&1
