@@ -43,6 +43,12 @@ DTYPE = np.float64
 WORKLOAD = "7pt-const-fp64-512^3-nt500-diamond"
 
 
+def workload_config():
+    """the workload, spelled identically by both arms (everything arm-specific goes under "detail")"""
+    return {"workload": WORKLOAD, "operator": "slot 1: 7-point constant-coefficient star", "precision": "fp64",
+            "domain_per_gpu": [NX, NY, NZ], "nt": NT, "stepper": "Diamond (ts 2), t_dim 7: nt rounds to 514, 513 steps executed"}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -124,20 +130,38 @@ def cpu_has_avx512():
         return False
 
 
-def reference_mwd_flags(threads, ny):
-    """pinned MWD parameters (the reference's auto-tuner does not finish in minutes):
-    1WD when the thread count allows one diamond per thread, else thread groups along z."""
+def reference_mwd_candidates(threads, ny):
+    """pinned MWD parameter sets (the reference's auto-tuner does not finish in minutes): 1WD with one
+    diamond per thread (at most diamonds-1 threads can work at a time), and thread groups along z that use every
+    core.  The caller times both on a short sample and keeps the faster one: the baseline must be the
+    reference's best pinned setting on this box, not a heuristic's."""
     t_dim = T_DIM
     conc = ny // ((t_dim + 1) * 2)          # diamonds per row (diamond_utils.c:900-901)
+    base = ["--target-kernel", KERNEL, "--target-ts", 2, "--mwd-type", 2, "--t-dim", t_dim]
+    cands = [(min(threads, max(1, conc - 1)), base + ["--thread-group-size", 1, "--num-wavefronts", 4])]
     tgs = 1
     while threads // tgs > max(1, conc - 1):
         tgs *= 2
-    threads = max(tgs, threads // tgs * tgs)
-    fl = ["--target-kernel", KERNEL, "--target-ts", 2, "--mwd-type", 2, "--t-dim", t_dim,
-          "--thread-group-size", tgs, "--num-wavefronts", max(4, tgs)]
     if tgs > 1:
-        fl += ["--thz", tgs, "--thx", 1, "--thy", 1]
-    return threads, fl
+        cands.append((max(tgs, threads // tgs * tgs),
+                      base + ["--thread-group-size", tgs, "--num-wavefronts", max(4, tgs), "--thz", tgs, "--thx", 1, "--thy", 1]))
+    return cands
+
+
+_REF_CHOICE = {}
+
+
+def _run_ref(exe, threads, fl, nz_sample, nt_sample, n_tests=1):
+    cmd = [exe, "--nx", NX, "--ny", NY, "--nz", nz_sample, "--nt", nt_sample, "--n-tests", n_tests,
+           "--verbose", 0] + fl
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="true", OMP_PLACES="cores")
+    t0 = time.perf_counter()
+    out = subprocess.run([str(c) for c in cmd], env=env, capture_output=True, text=True, timeout=1500)
+    dt = time.perf_counter() - t0
+    m = re.search(r"Total RANK0 MStencil/s MAX:\s*([0-9.eE+-]+)", out.stdout)
+    if not m:
+        raise RuntimeError("reference run failed: " + out.stdout[-400:] + out.stderr[-400:])
+    return float(m.group(1)) / 1e3, dt
 
 
 def run_reference_sample(nz_sample, nt_sample, n_tests=1):
@@ -159,19 +183,20 @@ def run_reference_sample(nz_sample, nt_sample, n_tests=1):
         lups = NX * NY * nz_sample * nt_sample
         return {"glups": lups / dt / 1e9, "kind": "port", "cores": threads, "seconds": dt,
                 "sample": f"oracle port, {NX}x{NY}x{nz_sample} x {nt_sample} steps"}
-    threads, fl = reference_mwd_flags(threads, NY)
-    cmd = [exe, "--nx", NX, "--ny", NY, "--nz", nz_sample, "--nt", nt_sample, "--n-tests", n_tests,
-           "--verbose", 0] + fl
-    env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="true", OMP_PLACES="cores")
-    t0 = time.perf_counter()
-    out = subprocess.run([str(c) for c in cmd], env=env, capture_output=True, text=True, timeout=1500)
-    dt = time.perf_counter() - t0
-    m = re.search(r"Total RANK0 MStencil/s MAX:\s*([0-9.eE+-]+)", out.stdout)
-    if not m:
-        raise RuntimeError("reference run failed: " + out.stdout[-400:] + out.stderr[-400:])
-    return {"glups": float(m.group(1)) / 1e3, "kind": "reference", "cores": threads, "seconds": dt,
+    if exe not in _REF_CHOICE:
+        cands = reference_mwd_candidates(threads, NY)
+        if len(cands) > 1:   # short probe of each pinned setting (same grid, 1/5 of the steps), keep the faster
+            probe = [(_run_ref(exe, th, fl, nz_sample, max(20, nt_sample // 5))[0], th, fl) for th, fl in cands]
+            best = max(probe, key=lambda x: x[0])
+            _REF_CHOICE[exe] = (best[1], best[2], {" ".join(str(x) for x in fl): round(g, 2) for g, th, fl in probe})
+        else:
+            _REF_CHOICE[exe] = (cands[0][0], cands[0][1], None)
+    threads, fl, probe_log = _REF_CHOICE[exe]
+    glups, dt = _run_ref(exe, threads, fl, nz_sample, nt_sample, n_tests)
+    return {"glups": glups, "kind": "reference", "cores": threads, "seconds": dt,
             "sample": f"{os.path.basename(exe)} {NX}x{NY}x{nz_sample}, nt {nt_sample} (diamond-rounded), "
-                      f"MWD pinned: {' '.join(str(x) for x in fl)}"}
+                      f"MWD pinned: {' '.join(str(x) for x in fl)}"
+                      + (f"; probed GLUP/s per setting: {probe_log}" if probe_log else "")}
 
 
 def main_reference(args):
@@ -187,11 +212,78 @@ def main_reference(args):
     line = {"impl": "reference", "metric": "GLUP/s", "value": v, "unit": "GLUP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(secs),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": last["sample"]},
+            "config": workload_config(), "detail": {"sample": last["sample"]},
             "cpu_baseline": {"value": v, "unit": "GLUP/s", "cores": last["cores"], "kind": last["kind"],
                              "sample": last["sample"]},
             "e2e": {"value": v, "unit": "GLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# parity check of the run's own rank layout: small z-slab problems through the same C ABI, a communicator made the
+# same way as the timed one, slabs gathered to rank 0 and compared byte for byte with the CPU oracle on the global
+# domain -- the GPU analogue of the reference's aggregate_subdomains + compare (src/verification.c:955-1040).
+# The oracle is the checker here, never the thing timed.
+# ------------------------------------------------------------------------------------------------
+def parity_check(G, dist, world, rank, local, halo_push, halo_copy=False):
+    from oracle import girih_oracle as O
+    cases = [
+        # name, kernel, dtype, global interior, stepper ("fused", nsteps, T) / ("single", nsteps, overlap), push
+        ("k1-fp64-diamond-T4", 1, np.float64, (96, 64, 48 * world), ("fused", 21, 4), False),
+        ("k1-fp32-diamond-T3-uneven-slabs", 1, np.float32, (70, 41, 19 * world + (3 if world > 1 else 0)), ("fused", 10, 3), False),
+        ("k0-fp32-halo-first", 0, np.float32, (64, 40, 32 * world), ("single", 8, 1), False),
+        ("k5-fp64-diamond-T3", 5, np.float64, (70, 41, 24 * world), ("fused", 11, 3), False),
+    ]
+    if world > 1 and halo_push:
+        cases.append(("k1-fp64-diamond-T4-halo-push", 1, np.float64, (96, 64, 48 * world), ("fused", 18, 4), "halo_push"))
+    if world > 1 and halo_copy:
+        cases.append(("k1-fp64-diamond-T4-halo-copy", 1, np.float64, (96, 64, 48 * world), ("fused", 18, 4), "halo_copy"))
+        cases.append(("k0-fp32-halo-first-halo-copy", 0, np.float32, (64, 40, 32 * world), ("single", 8, 1), "halo_copy"))
+    results = []
+    for name, kernel, dt, gst, (mode, nsteps, par), push in cases:
+        pb = G.make_problem(kernel, gst, dt, rank=rank, nranks=world)
+        s = G.GpuStepper(kernel, pb.stencil, pb.shape, dt, device=local, rank=rank, nranks=world)
+        if world > 1:
+            obj = [G.GpuStepper.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(obj, src=0)
+            s.comm_init(obj[0])
+            if push:
+                blobs = [None] * world
+                dist.all_gather_object(blobs, s.peer_export())
+                if rank > 0:
+                    s.peer_attach(0, blobs[rank - 1])
+                if rank + 1 < world:
+                    s.peer_attach(1, blobs[rank + 1])
+                s.set_option(push, 1)
+        s.upload(pb)
+        if mode == "fused":
+            s.run_fused(nsteps, par)
+        else:
+            s.run_single(nsteps, overlap=bool(par))
+        s.download(pb.U1, pb.U2)
+        r, lnz = pb.r, pb.stencil[2]
+        mine = (pb.gb[2], pb.U1[r:r + lnz].copy(), pb.U2[r:r + lnz].copy())
+        if world > 1:
+            got = [None] * world if rank == 0 else None
+            dist.gather_object(mine, got, dst=0)
+            if push:
+                s.peer_detach()
+                dist.barrier()
+        else:
+            got = [mine]
+        s.close()
+        if rank == 0:
+            ob = O.make_problem(kernel, gst, dt)
+            O.run_steps(ob, nsteps)
+            ok = True
+            for z0, u1, u2 in got:
+                n = u1.shape[0]
+                ok = ok and u1.tobytes() == ob.U1[z0 + r:z0 + r + n].tobytes() and u2.tobytes() == ob.U2[z0 + r:z0 + r + n].tobytes()
+            results.append({"case": name, "global_domain": list(gst), "steps": nsteps, "bit_exact": bool(ok)})
+    if rank != 0:
+        return None
+    return {"nranks": world, "bit_exact": all(c["bit_exact"] for c in results), "cases": results,
+            "against": "oracle/girih_oracle.c on the global domain (pinned to the reference, tests/test_oracle_vs_reference.py)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -210,10 +302,8 @@ def main_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
     torch.cuda.set_device(local)
-    # NCCL writes its banner ("NCCL version ...") and debug lines to stdout: send them to a file so that
-    # stdout carries exactly the one JSON line
-    os.environ["NCCL_DEBUG"] = os.environ.get("GIRIH_NCCL_DEBUG", "WARN")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/girih_bench_nccl_%h_%p.log")
+    # NCCL's own log settings (NCCL_DEBUG, NCCL_DEBUG_FILE) are left exactly as the caller set them: the driver reads
+    # the communicator's init lines.  The JSON line is printed last, on a line of its own.
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -236,15 +326,15 @@ def main_ours(args):
         obj = [G.GpuStepper.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(obj, src=0)
         s.comm_init(obj[0])
-        if args.halo_push:
-            # halo push over NVLink peer memory: every rank maps its z neighbours' arrays (CUDA IPC between processes)
+        if args.halo_push or args.halo_copy:
+            # halo push / copy over NVLink peer memory: every rank maps its z neighbours' arrays (CUDA IPC between processes)
             blobs = [None] * world
             dist.all_gather_object(blobs, s.peer_export())
             if rank > 0:
                 s.peer_attach(0, blobs[rank - 1])
             if rank + 1 < world:
                 s.peer_attach(1, blobs[rank + 1])
-            s.set_option("halo_push", 1)
+            s.set_option("halo_copy" if args.halo_copy else "halo_push", 1)
     s.upload(pb)
     contract = int(args.arith == "contract")
     s.set_option("contract", contract)
@@ -382,10 +472,11 @@ def main_ours(args):
             except Exception as e:   # noqa: BLE001
                 cpu_base = {"value": None, "unit": "GLUP/s", "cores": host_threads(), "kind": "reference",
                             "sample": f"failed: {e}"}
-    if world > 1 and args.halo_push:   # importers unmap before any exporter frees
+    if world > 1 and (args.halo_push or args.halo_copy):   # importers unmap before any exporter frees
         s.peer_detach()
         barrier()
     s.close()
+    parity = None if args.no_parity_check else parity_check(G, dist, world, rank, local, bool(args.halo_push), bool(args.halo_copy))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -394,7 +485,8 @@ def main_ours(args):
     line = {"metric": "GLUP/s", "value": value, "unit": "GLUP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_domain": list(gst), "nt": nt_eff, "steps_executed": nsteps,
+            "config": workload_config(),
+            "detail": {"global_domain": list(gst), "nt": nt_eff, "steps_executed": nsteps,
                        "stepper": "Diamond (ts 2)", "fused_steps_per_pass": info["tfuse"],
                        "arith": ("contract: the FMAs gcc -O3 -mfma emits for the reference, bit-exact vs that build"
                                  if contract else
@@ -404,18 +496,23 @@ def main_ours(args):
                        "halo_exchange": (None if world == 1 else
                                          {"ms_per_step_max_over_ranks": comm_ms / args.steps,
                                           "compute_ms_per_step_per_rank": per_rank_compute,
-                                          "overlap_with_interior": bool(args.overlap),
-                                          "halo_push": bool(args.halo_push)}),
+                                          "overlap_with_interior": bool(args.overlap or args.halo_copy),
+                                          "halo_push": bool(args.halo_push), "halo_copy": bool(args.halo_copy)}),
                        "wall_s": wall},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "GLUP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "mode": args.e2e_mode},
             "gpu_launches": launches, "roofline": roof}
+    if parity is not None:
+        line["parity_check"] = parity
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
     if other is not None:
         line["other_arith"] = other
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    print("\n" + json.dumps(line), flush=True)
+    if parity is not None and not parity["bit_exact"]:
+        raise SystemExit("parity_check failed: " + json.dumps(parity))
 
 
 def main():
@@ -434,12 +531,18 @@ def main():
                     help="N>1: fused passes store their boundary planes straight into the neighbours' halos over NVLink "
                          "(girih_gpu_peer_export/_attach, option halo_push) instead of NCCL exchanges between passes; "
                          "opt-in until validated on hardware")
+    ap.add_argument("--halo-copy", type=int, default=0,
+                    help="N>1: overlapped schedule (outer parts of the slab first) with the halos copied into the neighbours' "
+                         "halo planes by the copy engines (cudaMemcpyAsync into IPC-mapped peer memory + flags) under the sweep "
+                         "of the inner part: no SM is taken from the sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-mode", default="sequential", choices=["sequential", "pipelined"],
-                    help="sequential: H2D, stepper, D2H one after the other for every step (default). pipelined: the steps "
-                         "are independent jobs; the H2D of the next one and the D2H of the previous one run on the copy "
-                         "engines under the sweeps of the current one (girih_gpu_prefetch_fields / _download_async); "
-                         "every copy still lies inside the timed region")
+    ap.add_argument("--no-parity-check", action="store_true",
+                    help="skip the small oracle-compared runs on this rank layout that follow the timed legs")
+    ap.add_argument("--e2e-mode", default="pipelined", choices=["sequential", "pipelined"],
+                    help="pipelined (default; validated on B200 in round 2): the steps are independent jobs; the H2D of the "
+                         "next one and the D2H of the previous one run on the copy engines under the sweeps of the current "
+                         "one (girih_gpu_prefetch_fields / _download_async); every copy still lies inside the timed "
+                         "region.  sequential: H2D, stepper, D2H one after the other for every step")
     args = ap.parse_args()
     if args.impl == "reference":
         main_reference(args)

@@ -273,6 +273,11 @@ class GpuStepper:
         self._lib.girih_gpu_last_launch_info(self._ctx, *[C.byref(x) for x in v])
         return {"kernels": v[0].value, "passes": v[1].value, "steps": v[2].value, "tfuse": v[3].value}
 
+    def stat(self, key: str) -> int:
+        v = C.c_longlong()
+        self._check(self._lib.girih_gpu_get_stat(self._ctx, key.encode(), C.byref(v)), "girih_gpu_get_stat")
+        return v.value
+
     def scan_u1(self):
         a, b = C.c_uint64(), C.c_uint64()
         self._check(self._lib.girih_gpu_scan_u1(self._ctx, C.byref(a), C.byref(b)), "girih_gpu_scan_u1")

@@ -90,6 +90,7 @@ struct girih_gpu_ctx {
   std::vector<EvPair> comm_ev;
   size_t comm_ev_used = 0;
   bool uploaded = false, frames_equal = true, static_halo_done = false;
+  bool frames_dirty = false;   // fields were replaced on the device since frames_equal was evaluated (upload_fields / commit_fields)
   // NCCL
   ncclComm_t comm = nullptr;
   // options
@@ -114,9 +115,19 @@ struct girih_gpu_ctx {
   int peer_nz[2] = {0, 0};
   bool peer_ipc[2] = {false, false};      // mapped with cudaIpcOpenMemHandle (to be closed)
   int opt_push = 0;
+  int opt_copy = 0;                       // option "halo_copy": overlapped passes move their halos with the copy engines
   int push_seq = 0;                       // passes signalled so far (the same number on every rank)
   int push_planes = 0;                    // planes the pass being launched pushes to each neighbour (0 = none)
   cudaEvent_t ev_in_ready = nullptr, ev_in_free = nullptr, ev_out_ready = nullptr, ev_out_free = nullptr;
+  // exact-tiled fused sweep (kernels_r1x.cuh): inbound edge slots of the co-resident CTAs (they stay in L2), the running
+  // slot tag and the flag a CTA raises when a neighbour tile never delivered
+  unsigned char *d_xbuf = nullptr;
+  size_t xbuf_bytes = 0;
+  unsigned xseq = 0;
+  int *d_xerr = nullptr;
+  int nsm = 148;
+  bool xbuf_used = false;
+  long long n_exact = 0, n_fused = 0;   // fused passes on exact tiles / all fused passes, since creation
   char err[512] = "";
 };
 
@@ -214,7 +225,7 @@ extern "C" int girih_gpu_create(girih_gpu_ctx **out, int device, int target_kern
     e = cudaMalloc(&c->dCoef, bytes * c->kd.n_coef_arrays);
     if (e == cudaSuccess) e = cudaMemset(c->dCoef, 0, bytes * c->kd.n_coef_arrays);
   }
-  if (e == cudaSuccess) e = cudaMalloc(&c->d_scan, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_scan, 4 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking);
   if (e == cudaSuccess) {   // the exchange stream outranks the sweep: its few CTAs go first when SM slots free up
     int lo = 0, hi = 0;
@@ -244,6 +255,8 @@ extern "C" void girih_gpu_destroy(girih_gpu_ctx *c) {
   if (c->dU3) cudaFree(c->dU3);
   if (c->dCoef) cudaFree(c->dCoef);
   if (c->d_scan) cudaFree(c->d_scan);
+  if (c->d_xbuf) cudaFree(c->d_xbuf);
+  if (c->d_xerr) cudaFree(c->d_xerr);
   if (c->d_stage) cudaFree(c->d_stage);
   if (c->d_pack) cudaFree(c->d_pack);
   if (c->s_h2d) cudaStreamSynchronize(c->s_h2d);
@@ -296,6 +309,7 @@ extern "C" int girih_gpu_set_option(girih_gpu_ctx *c, const char *key, int value
   else if (!strcmp(key, "contract")) c->opt_contract = (value != 0);
   else if (!strcmp(key, "halo_group")) c->opt_halo_group = value;
   else if (!strcmp(key, "halo_push")) c->opt_push = value;
+  else if (!strcmp(key, "halo_copy")) c->opt_copy = value;
   else return fail(c, GIRIH_ERR_ARG, "unknown option '%s'", key);
   return GIRIH_OK;
 }
@@ -366,6 +380,7 @@ extern "C" int girih_gpu_upload(girih_gpu_ctx *c, const void *U1, const void *U2
     c->cc[m] = (c->es == 8) ? ((const double *)coef)[m] : (double)((const float *)coef)[m];
   c->frames_equal = (c->es == 8) ? frames_match(c, (const double *)U1, (const double *)U2)
                                  : frames_match(c, (const float *)U1, (const float *)U2);
+  c->frames_dirty = false;
   c->uploaded = true;
   c->static_halo_done = false;
   return GIRIH_OK;
@@ -432,6 +447,56 @@ extern "C" int girih_gpu_upload_fields(girih_gpu_ctx *c, const void *U1, const v
   if (U1 && (rc = fast_copy(c, c->dU[0], const_cast<void *>(U1), true))) return rc;
   if (U2 && (rc = fast_copy(c, c->dU[1], const_cast<void *>(U2), true))) return rc;
   CU(cudaStreamSynchronize(c->s_comp));
+  if (U1 || U2) c->frames_dirty = true;   // the frames travelled too: re-evaluated on the device before the next fused run
+  return GIRIH_OK;
+}
+
+// Do U1 and U2 agree on the Dirichlet frame?  Device-side twin of frames_match() for fields that were replaced
+// on the device (upload_fields, commit_fields): one flag word, read back only when a fused run needs the answer.
+__device__ __forceinline__ bool same_bits(double x, double y) {
+  return *reinterpret_cast<const unsigned long long *>(&x) == *reinterpret_cast<const unsigned long long *>(&y);
+}
+__device__ __forceinline__ bool same_bits(float x, float y) {
+  return *reinterpret_cast<const unsigned *>(&x) == *reinterpret_cast<const unsigned *>(&y);
+}
+template <typename R>
+__global__ void k_frame_diff(DevGrid g, const R *__restrict__ a, const R *__restrict__ b, int hy, int hz, int zfirst,
+                             int zlast, unsigned long long *flag) {
+  const int r = g.r, w = g.nx + 2 * r;
+  const long long rows = (long long)hy * hz;
+  bool diff = false;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = (int)(row % hy), z = (int)(row / hy);
+    const bool whole = (zfirst && z < r) || (zlast && z >= hz - r) || (y < r) || (y >= hy - r);
+    const long long o = ((long long)(z + g.Z0 - r) * g.ny_dev + (y + g.Y0 - r)) * g.px + (g.X0 - r);
+    if (whole) {
+      for (int x = threadIdx.x; x < w; x += blockDim.x) diff |= !same_bits(a[o + x], b[o + x]);
+    } else if ((int)threadIdx.x < 2 * r) {
+      const int x = (int)threadIdx.x < r ? (int)threadIdx.x : w - 2 * r + (int)threadIdx.x;
+      diff |= !same_bits(a[o + x], b[o + x]);
+    }
+  }
+  if (diff) *flag = 1ull;
+}
+
+static int refresh_frames_equal(girih_gpu_ctx *c) {
+  if (!c->frames_dirty) return GIRIH_OK;
+  unsigned long long *flag = c->d_scan + 2;
+  CU(cudaMemsetAsync(flag, 0, sizeof(*flag), c->s_comp));
+  const int zf = c->coords[2] == 0, zl = c->coords[2] == c->dims[2] - 1;
+  if (c->es == 8) {
+    auto k = k_frame_diff<double>;
+    GIRIH_LAUNCH(k, 148 * 8, 128, 0, c->s_comp, c->g, (const double *)c->dU[0], (const double *)c->dU[1], c->hshape[1], c->hshape[2], zf, zl, flag);
+  } else {
+    auto k = k_frame_diff<float>;
+    GIRIH_LAUNCH(k, 148 * 8, 128, 0, c->s_comp, c->g, (const float *)c->dU[0], (const float *)c->dU[1], c->hshape[1], c->hshape[2], zf, zl, flag);
+  }
+  CU(cudaGetLastError());
+  unsigned long long h = 0;
+  CU(cudaMemcpyAsync(&h, flag, sizeof(h), cudaMemcpyDeviceToHost, c->s_comp));
+  CU(cudaStreamSynchronize(c->s_comp));
+  c->frames_equal = (h == 0);
+  c->frames_dirty = false;
   return GIRIH_OK;
 }
 
@@ -507,6 +572,7 @@ extern "C" int girih_gpu_commit_fields(girih_gpu_ctx *c) {
     if (!c->in_pending[i]) continue;
     CU(launch_repitch(c, c->dU[i], c->d_in[i], true));
     c->in_pending[i] = false;
+    c->frames_dirty = true;
   }
   CU(cudaEventRecord(c->ev_in_free, c->s_comp));
   return GIRIH_OK;
@@ -648,6 +714,23 @@ extern "C" int girih_gpu_peer_detach(girih_gpu_ctx *c) {
 static bool push_enabled(const girih_gpu_ctx *c, int Tmax) {
   if (!c->opt_push || c->nranks == 1 || xy_decomposed(c) || c->kernel != 1 || c->opt_variant == 1 || c->opt_tile != 0) return false;
   if (Tmax * c->g.r > c->nz_min) return false;
+  if (Tmax <= 1) return false;   // single-step runs (ts 0/1) exchange through NCCL: nothing is fused, nothing to hide
+  const bool need_dn = neighbour(c, 2, -1) >= 0, need_up = neighbour(c, 2, +1) >= 0;
+  return c->d_flags && (!need_dn || c->peer_flags[0]) && (!need_up || c->peer_flags[1]);
+}
+
+// Halo copy: the overlapped ("halo-first") schedule with the exchange done by the COPY ENGINES instead of NCCL's
+// SM kernels.  After the sweep of the two outer parts of the slab, the planes the neighbours read in the next pass are
+// copied straight into their halo planes (peer memory mapped by girih_gpu_peer_attach) on the comm stream, followed by a
+// one-thread kernel that raises the neighbours' flag words; the sweep of the inner part runs meanwhile on every SM (an
+// NCCL kernel in that place takes SMs from a sweep that fills whole waves of 148 and pushes its tail into an extra wave).
+// The next pass starts its outer parts once both neighbours' flags have arrived.  Ordering argument:
+//   RAW  the neighbour's next outer sweep waits for my flag, raised behind my copy in stream order
+//   WAR  my copy overwrites halo planes the neighbour last read in its previous outer sweep, which finished before the
+//        neighbour signalled the data I waited for; my own next-but-one outer sweep overwrites the planes this copy
+//        reads and therefore waits for the copy's event
+static bool copy_enabled(const girih_gpu_ctx *c) {
+  if (!c->opt_copy || c->nranks == 1 || xy_decomposed(c)) return false;
   const bool need_dn = neighbour(c, 2, -1) >= 0, need_up = neighbour(c, 2, +1) >= 0;
   return c->d_flags && (!need_dn || c->peer_flags[0]) && (!need_up || c->peer_flags[1]);
 }
@@ -900,6 +983,30 @@ static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb
   sl.variant = c->opt_variant;
   sl.contract = c->opt_contract;
   sl.stream = c->s_comp;
+  if (tile_is_exact(sl.tile) && g.r == 1 && T > 1) {
+    if (!c->d_xbuf) {   // 48 KB of edge slots per resident CTA, zeroed once: tag 0 is never used
+      cudaDeviceGetAttribute(&c->nsm, cudaDevAttrMultiProcessorCount, c->device);
+      const size_t bytes = (size_t)c->nsm * 48 * 1024;
+      if (cudaMalloc((void **)&c->d_xbuf, bytes) == cudaSuccess && cudaMalloc((void **)&c->d_xerr, sizeof(int)) == cudaSuccess) {
+        cudaMemsetAsync(c->d_xbuf, 0, bytes, c->s_comp);
+        cudaMemsetAsync(c->d_xerr, 0, sizeof(int), c->s_comp);
+        c->xbuf_bytes = bytes;
+        c->xseq = 0;
+      } else {
+        (void)cudaGetLastError();
+      }
+    }
+    if (c->xseq > 0xf0000000u) {   // tags are 32 bits: start over from clean slots long before they wrap
+      cudaMemsetAsync(c->d_xbuf, 0, c->xbuf_bytes, c->s_comp);
+      c->xseq = 0;
+    }
+    sl.xbuf = c->xbuf_bytes ? c->d_xbuf : nullptr;
+    sl.xbuf_bytes = c->xbuf_bytes;
+    sl.xseq = &c->xseq;
+    sl.xerr = c->d_xerr;
+    sl.nsm = c->nsm;
+    c->xbuf_used = c->xbuf_bytes != 0;
+  }
   if (c->push_planes > 0) {   // this pass also stores its boundary planes into the neighbours' halos (run_passes)
     const size_t plane_b = (size_t)g.pxy * c->es;
     if (c->peer_U[1][dst]) {   // my planes [Z0+nz-D, Z0+nz) -> upper neighbour's planes [Z0-D, Z0): shift by -nz
@@ -913,7 +1020,13 @@ static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb
   }
   c->n_kernels++;
   if (c->kernel == 7) return T == 1 ? launch_box(c->es, sl) : cudaErrorInvalidValue;
-  if (g.r == 1) return launch_r1(c->kernel, c->es, T, sl);
+  if (g.r == 1) {
+    const unsigned seq_before = c->xseq;
+    const cudaError_t e = launch_r1(c->kernel, c->es, T, sl);
+    if (T > 1) c->n_fused++;
+    if (c->xseq != seq_before) c->n_exact++;   // the exact-tile launcher consumed slot tags: it ran
+    return e;
+  }
   if (T != 1) return cudaErrorInvalidValue;
   return launch_r4(c->kernel, c->es, sl);
 }
@@ -942,6 +1055,7 @@ static int begin_run(girih_gpu_ctx *c) {
   c->n_kernels = c->n_passes = c->n_steps = 0;
   c->comm_ev_used = 0;
   c->ms_compute = c->ms_comm = c->ms_total = 0;
+  if (c->d_flags) CU(cudaMemsetAsync(c->d_flags + 2, 0, sizeof(int), c->s_comp));   // "a halo-push wait gave up" is per run
   CU(cudaEventRecord(c->ev_t0, c->s_comp));
   return GIRIH_OK;
 }
@@ -949,6 +1063,14 @@ static int end_run(girih_gpu_ctx *c) {
   CU(cudaEventRecord(c->ev_t1, c->s_comp));
   CU(cudaStreamSynchronize(c->s_comp));
   CU(cudaStreamSynchronize(c->s_comm));
+  if (c->xbuf_used) {   // did a tile of the exact-tiled sweep give up on a neighbour tile?
+    int gave_up = 0;
+    CU(cudaMemcpy(&gave_up, c->d_xerr, sizeof(int), cudaMemcpyDeviceToHost));
+    if (gave_up) {
+      CU(cudaMemset(c->d_xerr, 0, sizeof(int)));
+      return fail(c, GIRIH_ERR_STATE, "exact-tiled sweep: a tile waited for a neighbour's edge values beyond the limit");
+    }
+  }
   if (c->d_flags && c->opt_push) {   // did a halo-push wait give up on a neighbour?
     int gave_up = 0;
     CU(cudaMemcpy(&gave_up, c->d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1028,10 +1150,13 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
   int Tmax = 1;
   for (int s : sizes) Tmax = std::max(Tmax, s);
   if (xy_decomposed(c)) overlap = false;   // x/y faces are exchanged between whole steps only
+  const bool copy = copy_enabled(c);       // halo copy: the overlapped schedule, halos moved by the copy engines
+  if (copy) overlap = true;
   const bool push = !overlap && push_enabled(c, Tmax);   // halo push: the sweep itself feeds the neighbours' halos
   const int group = push ? 1 : halo_group(c, Tmax, overlap);
   std::vector<int> depth;
   plan_exchanges(sizes, r, c->halo_max, group, depth);
+  bool copy_live = false;   // the halos of `cur` were delivered by the neighbours' copies (wait for their flags)
   if (group > 1) {
     // the Dirichlet frame cells of the deep-halo planes are never written by a kernel: bring them (with
     // the planes) into BOTH arrays once; later exchanges and extended sweeps keep them
@@ -1093,6 +1218,14 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
     if (c->nranks > 1 && ready < T * r) {
       if ((rc = timed_exchange(c, c->dU[src], T * r))) return rc;
     }
+    if (copy_live) {
+      // the halos of `src` were copied in by the neighbours during their previous pass: wait for both flags
+      const bool wdn = neighbour(c, 2, -1) >= 0, wup = neighbour(c, 2, +1) >= 0;
+      GIRIH_LAUNCH(k_flag_wait, 1, 1, 0, c->s_comp, (volatile int *)c->d_flags, (int)wdn, (int)wup, c->push_seq, 20000000000LL);
+      CU(cudaGetLastError());
+      c->n_kernels++;
+      copy_live = false;
+    }
     const int nd = (p + 1 < sizes.size()) ? sizes[p + 1] * r : r;   // halo depth the next pass needs
     // (decided on the thinnest slab of the run so that every rank takes the same branch: the two branches
     // exchange at different points)
@@ -1101,6 +1234,7 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
       // the 2T-plane pipeline fill for a few planes), then the halo exchange of the new level runs under
       // the sweep of the inner half
       const int zq = std::max(nd, g.nz / 4);
+      const bool need_dn = neighbour(c, 2, -1) >= 0, need_up = neighbour(c, 2, +1) >= 0;
       CU(launch_pass(c, T, src, dst, zb, zb + zq, ze - zq, ze));
       CU(cudaEventRecord(c->ev_y, c->s_comp));
       CU(cudaStreamWaitEvent(c->s_comm, c->ev_y, 0));
@@ -1112,10 +1246,27 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
       }
       EvPair &q = c->comm_ev[c->comm_ev_used++];
       CU(cudaEventRecord(q.a, c->s_comm));
-      if ((rc = exchange_z(c, c->dU[dst], nd, c->s_comm))) return rc;
+      if (copy) {
+        const size_t plane_b = (size_t)g.pxy * c->es, bytes = (size_t)nd * plane_b;
+        char *mine = (char *)c->dU[dst];
+        if (need_up)   // my top nd planes -> the upper neighbour's planes [Z0 - nd, Z0)
+          CU(cudaMemcpyAsync((char *)c->peer_U[1][dst] + (size_t)(g.Z0 - nd) * plane_b, mine + (size_t)(ze - nd) * plane_b, bytes,
+                             cudaMemcpyDeviceToDevice, c->s_comm));
+        if (need_dn)   // my lowest nd planes -> the lower neighbour's planes [Z0 + nz', Z0 + nz' + nd)
+          CU(cudaMemcpyAsync((char *)c->peer_U[0][dst] + (size_t)(g.Z0 + c->peer_nz[0]) * plane_b, mine + (size_t)zb * plane_b, bytes,
+                             cudaMemcpyDeviceToDevice, c->s_comm));
+        c->push_seq++;
+        c->n_kernels++;
+        GIRIH_LAUNCH(k_flag_signal, 1, 1, 0, c->s_comm, (volatile int *)(need_dn ? c->peer_flags[0] + 1 : nullptr),
+                     (volatile int *)(need_up ? c->peer_flags[1] + 0 : nullptr), c->push_seq);
+        CU(cudaGetLastError());
+        copy_live = true;
+      } else {
+        if ((rc = exchange_z(c, c->dU[dst], nd, c->s_comm))) return rc;
+      }
       CU(cudaEventRecord(q.b, c->s_comm));
       CU(launch_pass(c, T, src, dst, zb + zq, ze - zq));
-      CU(cudaStreamWaitEvent(c->s_comp, q.b, 0));
+      CU(cudaStreamWaitEvent(c->s_comp, q.b, 0));   // my next-but-one outer sweep overwrites what this exchange reads
       ready = nd;
     } else {
       CU(launch_pass(c, T, src, dst, zb, ze));
@@ -1206,7 +1357,9 @@ extern "C" int girih_gpu_run_fused(girih_gpu_ctx *c, int nsteps, int tfuse) {
   if (T <= 0) T = c->tuned_tfuse > 0 ? c->tuned_tfuse : default_tfuse(c);
   T = std::min(T, c->kd.max_tfuse);
   if (c->opt_variant == 1 || c->kernel == 7 || xy_decomposed(c)) T = 1;
+  CU(cudaSetDevice(c->device));
   if (c->nranks > 1) T = std::min(T, std::max(1, c->nz_min / std::max(1, c->g.r)));   // same depth on every rank
+  if (T > 1) { int frc = refresh_frames_equal(c); if (frc) return frc; }
   if (T > 1 && !c->frames_equal) return fail(c, GIRIH_ERR_FRAME, "%s", girih_gpu_strerror(GIRIH_ERR_FRAME));
   int rc;
   if ((rc = begin_run(c))) return rc;
@@ -1240,8 +1393,9 @@ extern "C" int girih_gpu_step_box(girih_gpu_ctx *c, int dst, int xb, int yb, int
 static int time_pass_local(girih_gpu_ctx *c, int tfuse, int reps, double *ms_per_pass) {
   int T = std::max(1, std::min(tfuse, c->kd.max_tfuse));
   if (c->opt_variant == 1 || c->kernel == 7) T = 1;
-  if (T > 1 && !c->frames_equal) return fail(c, GIRIH_ERR_FRAME, "%s", girih_gpu_strerror(GIRIH_ERR_FRAME));
   CU(cudaSetDevice(c->device));
+  if (T > 1) { int frc = refresh_frames_equal(c); if (frc) return frc; }
+  if (T > 1 && !c->frames_equal) return fail(c, GIRIH_ERR_FRAME, "%s", girih_gpu_strerror(GIRIH_ERR_FRAME));
   c->n_kernels = 0;
   const DevGrid &g = c->g;
   int cur = 1;
@@ -1297,6 +1451,7 @@ extern "C" int girih_gpu_autotune(girih_gpu_ctx *c, int fused, int verbose, int 
   const int saved_tile = c->opt_tile;
   const double lups = (double)c->g.nx * c->g.ny * c->g.nz;
   int Tmax = fused ? c->kd.max_tfuse : 1;
+  { int frc = refresh_frames_equal(c); if (frc) return frc; }
   if (c->opt_variant == 1 || c->kernel == 7 || !c->frames_equal) Tmax = 1;
   if (c->nranks > 1) Tmax = std::min(Tmax, std::max(1, c->nz_min / std::max(1, c->g.r)));
   cudaEvent_t e0, e1;
@@ -1348,6 +1503,13 @@ extern "C" int girih_gpu_last_elapsed_ms(girih_gpu_ctx *c, double *compute_ms, d
   if (compute_ms) *compute_ms = c->ms_compute;
   if (comm_ms) *comm_ms = c->ms_comm;
   if (total_ms) *total_ms = c->ms_total;
+  return GIRIH_OK;
+}
+extern "C" int girih_gpu_get_stat(girih_gpu_ctx *c, const char *key, long long *value) {
+  if (!c || !key || !value) return GIRIH_ERR_ARG;
+  if (!strcmp(key, "exact_launches")) *value = c->n_exact;
+  else if (!strcmp(key, "fused_launches")) *value = c->n_fused;
+  else return fail(c, GIRIH_ERR_ARG, "unknown stat '%s'", key);
   return GIRIH_OK;
 }
 extern "C" int girih_gpu_last_launch_info(girih_gpu_ctx *c, int *n_kernels, int *n_passes, int *n_steps, int *tfuse_used) {

@@ -2,9 +2,16 @@
 // inst_r1_k*_f*.cu translation units.
 #pragma once
 #include <algorithm>
+#ifdef GIRIH_R1X_TRACE
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+#endif
 
 #include "kernels_r1.cuh"
 #include "kernels_r1_march.cuh"
+#include "kernels_r1x.cuh"
 #include "launch.h"
 
 namespace girih {
@@ -68,9 +75,85 @@ static cudaError_t launch_r1_t(const StreamLaunch &s) {
   return cudaGetLastError();
 }
 
+// Exact (non-overlapping) tiles with edge hand-off between co-resident CTAs (kernels_r1x.cuh).  Needs one resident CTA
+// per tile and z chunk: cudaErrorNotSupported tells the caller to take the overlapped-tile kernel instead.
+template <int K, typename R, int T, int PY, int NW, bool FM = false>
+static cudaError_t launch_r1x_t(const StreamLaunch &s) {
+  if constexpr (sizeof(R) != 8 || T < 3) {
+    return cudaErrorNotSupported;
+  } else {
+    using Cfg = R1xCfg<R, T, PY, NW>;
+    const DevGrid &g = s.g;
+    if (s.xbuf == nullptr || s.xseq == nullptr || s.ze1 > s.zb1 || s.push_up != nullptr || s.push_dn != nullptr)
+      return cudaErrorNotSupported;
+    const int ntx = (g.nx + Cfg::WX - 1) / Cfg::WX, nty = (g.ny + Cfg::H - 1) / Cfg::H, nz = s.ze0 - s.zb0;
+    const long long tiles = (long long)ntx * nty;
+    if (nz < 1 || tiles > s.nsm) return cudaErrorNotSupported;
+    // z chunks: as many as stay co-resident, each at least 4T planes long (a chunk pays 2T planes of pipeline fill)
+    int nch = (int)std::min<long long>(s.nsm / tiles, std::max(1, nz / (4 * T)));
+    if (s.zchunk > 0) nch = std::min(nch, std::max(1, (nz + s.zchunk - 1) / s.zchunk));
+    const int zchunk = (nz + nch - 1) / nch;
+    nch = (nz + zchunk - 1) / zchunk;
+    if ((size_t)(tiles * nch) * Cfg::TILE_BYTES > s.xbuf_bytes) return cudaErrorNotSupported;
+    R1xArgs<R> a;
+    a.g = g;
+    a.in = (const R *)s.in;
+    a.out = (R *)s.out;
+    a.coef = (const R *)s.coef;
+    a.coef_stride = s.coef_stride;
+    a.cc = make_cc<R>(s.cc);
+    a.zb0 = s.zb0;
+    a.ze0 = s.ze0;
+    a.zchunk = zchunk;
+    a.xbuf = s.xbuf;
+    a.err = s.xerr;
+    a.seq0 = *s.xseq;
+    auto kfn = k_r1x<K, R, T, PY, NW, FM>;
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    dim3 grid(ntx, nty, nch);
+#ifdef GIRIH_R1X_TRACE
+    static long long *d_trace = nullptr;
+    const size_t trace_n = (size_t)tiles * nch * 2 * 16 * T * 2;
+    if (!d_trace) cudaMalloc((void **)&d_trace, 148 * 2 * 16 * 8 * 2 * sizeof(long long));
+    cudaMemsetAsync(d_trace, 0, trace_n * sizeof(long long), s.stream);
+    a.trace = d_trace;
+#endif
+    e = GIRIH_LAUNCH_COOP(kfn, grid, dim3(32 * NW), Cfg::SMEM, s.stream, a);
+#ifdef GIRIH_R1X_TRACE
+    if (const char *path = getenv("GIRIH_R1X_TRACE_FILE")) {
+      cudaStreamSynchronize(s.stream);
+      std::vector<long long> h(trace_n);
+      cudaMemcpy(h.data(), d_trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost);
+      if (FILE *f = fopen(path, "wb")) {
+        const int hdr[4] = {ntx, nty, nch, T};
+        fwrite(hdr, sizeof(int), 4, f);
+        fwrite(h.data(), sizeof(long long), trace_n, f);
+        fclose(f);
+      }
+    }
+#endif
+    if (e == cudaErrorCooperativeLaunchTooLarge) {   // something else holds SMs: overlapped tiles need no co-residency
+      (void)cudaGetLastError();
+      return cudaErrorNotSupported;
+    }
+    if (e == cudaSuccess) *s.xseq += (unsigned)(zchunk + 2 * T) + 2u;   // tags of this launch: seq0 + 1 .. seq0 + nit
+    return e;
+  }
+}
+
 // tile shapes instantiated per (operator, precision, depth); "tile" option = PY*100 + NW
 template <int K, typename R, int T>
 static cudaError_t launch_r1_tile(const StreamLaunch &s) {
+  if constexpr (K == 1 && sizeof(R) == 8 && T >= 3) {
+    // exact tiles: 10000 + PY*100 + NW (slot 1, fp64); falls through to the overlapped tiles when the grid cannot be co-resident
+    if (tile_is_exact(s.tile)) {
+      cudaError_t e = cudaErrorNotSupported;
+      if (s.tile == 10408) e = s.contract ? launch_r1x_t<K, R, T, 4, 8, true>(s) : launch_r1x_t<K, R, T, 4, 8, false>(s);
+      if (s.tile == 10216) e = s.contract ? launch_r1x_t<K, R, T, 2, 16, true>(s) : launch_r1x_t<K, R, T, 2, 16, false>(s);
+      if (e != cudaErrorNotSupported) return e;
+    }
+  }
   if constexpr (K == 1) {   // halo push: default tile of slot 1 only (girih_cuda.cu requests it for nothing else)
     if (s.push_up != nullptr || s.push_dn != nullptr) {
       if constexpr (sizeof(R) == 8) return s.contract ? launch_r1_t<K, R, T, 4, 8, R1_FM | R1_PUSH>(s) : launch_r1_t<K, R, T, 4, 8, R1_PUSH>(s);
@@ -161,7 +244,10 @@ static cudaError_t launch_march_t(const StreamLaunch &s) {
 
 template <int K, typename R>
 static cudaError_t launch_r1_depth(int T, const StreamLaunch &s) {
-  if (T == 1 && s.variant != 2) {
+  // a pass that pushes its boundary planes into the neighbours' halos needs the fused-sweep kernel (R1_PUSH) also
+  // at depth 1: the marching kernel has no push stores
+  const bool pushes = (s.push_up != nullptr) || (s.push_dn != nullptr);
+  if (T == 1 && s.variant != 2 && !pushes) {
     if (s.contract) {
       if constexpr (K == 1 || K == 5) return launch_march_t<K, R, 4, 4, true>(s);
       else return launch_march_t<K, R, 2, 8, true>(s);

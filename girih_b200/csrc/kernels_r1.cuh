@@ -25,6 +25,11 @@
 #include "common.cuh"
 #include "stencil_expr.cuh"
 
+// kernels_r1x.cuh writes its loop body as nested lambdas that are too large for the inliner's own budget (a call would
+// put the register planes on the stack).  NOT applied to k_r1 below: forcing its lambdas costs 4% (measured, round 2:
+// 0.956 vs 0.917 ms per fp64 T = 4 pass; 254 instead of 248 registers and a different schedule)
+#define GIRIH_LAMBDA_INLINE __attribute__((always_inline))
+
 namespace girih {
 
 template <typename R> struct R1Args {

@@ -1,0 +1,433 @@
+// kernels_r1x.cuh -- temporally fused sweep of the radius-1 star operators on NON-OVERLAPPING tiles.
+//
+// k_r1 (kernels_r1.cuh) gives every CTA a tile that overlaps its neighbours by T*r points per side and
+// recomputes the overlap: at T = 4 a 64 x 32 tile keeps 65.6% of what it computes (56.5% at 512^2 with
+// the partial tiles).  This kernel is the GPU form of what GIRIH's diamond tiling is for
+// (src/kernels/diamond_ts.c:565-595, intra_diamond_get_info_std: yb, ye, b_inc, e_inc; the y extent of a
+// tile changes by r per level, stencils_1wf.ic:65-71) -- no point is computed twice -- expressed for a
+// machine whose "thread groups" are 148 co-resident CTAs with a 126 MB L2 between them:
+//
+//   * the x-y plane is cut into EXACT tiles of WX x H points (no overlap), one CTA per tile and z chunk,
+//     all CTAs of the launch co-resident (cooperative launch); a CTA streams along z with the same
+//     register pipeline as k_r1 (three rotating register planes per fused level, level l+1 one plane
+//     behind level l)
+//   * what a tile is missing at its rim -- for every level l < T the column left / right of the tile and
+//     the row above / below it, plane by plane -- is handed over by the neighbouring CTA as soon as it has
+//     produced it: the producer stores the values straight into the consumer's inbound slots in global
+//     memory (they live in L2), every 8-byte word carrying its own sequence tag (payload, tag) like
+//     NCCL's LL protocol, so there is no fence, no flag round trip and no barrier between CTAs; the
+//     consumer polls a slot until the tag of the iteration it needs shows up
+//   * a value is published in iteration g (stage l-1) and consumed in iteration g+1 (stage l): one whole
+//     iteration (~2300 cycles) of slack against an L2 round trip of ~600; slots are a ring of three
+//     generations, which the dependence chain makes sufficient
+//   * polling is spread over the warps and over the T stages of an iteration, one 16-byte slot per lane
+//     in flight: the load is issued at the start of a stage and checked at its end, i.e. its latency
+//     runs under the stage's arithmetic
+//   * tiles on the Dirichlet frame read the frame cells (which no level changes) from the input array
+//     instead
+//
+// fp64 only (one value + tags = one 16-byte slot).
+#pragma once
+#include "common.cuh"
+#include "kernels_r1.cuh"
+#include "stencil_expr.cuh"
+
+namespace girih {
+
+template <typename R> struct R1xArgs {
+  DevGrid g;
+  const R *__restrict__ in;
+  R *__restrict__ out;
+  const R *__restrict__ coef;
+  long long coef_stride;
+  ConstCoef<R> cc;
+  int zb0, ze0;          // output planes [zb0, ze0) (device z)
+  int zchunk;            // output planes per CTA (blockIdx.z)
+  unsigned char *xbuf;   // inbound edge slots, R1xCfg::TILE_BYTES per CTA (linear block index)
+  unsigned seq0;         // iteration g of this launch tags its slots with seq0 + g + 1
+  int *err;              // set to 1 when a poll gave up (a neighbour tile never delivered): the host reports it
+#ifdef GIRIH_R1X_TRACE
+  long long *trace;      // measurement build only: [cta][warp 0 / warp 3][iteration 96..111][stage][before / after the wait]
+#endif
+};
+
+template <typename R, int T, int PY, int NW> struct R1xCfg {
+  static_assert(sizeof(R) == 8, "fp64 only");
+  static constexpr int VX = Vec<R>::N;
+  static constexpr int WX = 32 * VX;
+  static constexpr int H = NW * PY;
+  static constexpr int NXS = 2 * PY;                       // x slots of one warp and level (both sides)
+  static constexpr int LEVEL_SLOTS = 2 * H + 2 * WX;       // [x-: H][x+: H][y-: WX][y+: WX]
+  static constexpr int RING_SLOTS = T * LEVEL_SLOTS;
+  static constexpr int RING = 3;
+  static constexpr size_t TILE_BYTES = (size_t)RING * RING_SLOTS * 16;
+  static constexpr size_t EDGE_BYTES = (size_t)T * 2 * (NW + 2) * 2 * WX * sizeof(R);
+  static constexpr size_t XS_BYTES = (size_t)NW * T * 2 * PY * sizeof(R);
+  static constexpr size_t SMEM = EDGE_BYTES + XS_BYTES;
+  static_assert(T >= 2 && NW >= 2 && NXS <= 32, "one x slot per lane and stage; first and last warp are distinct");
+};
+
+// ---- LL slots: {payload lo, tag, payload hi, tag}; each 8-byte half is written / read atomically ----------
+constexpr unsigned R1X_SPIN_LIMIT = 1u << 22;   // polls (~0.3 us each) before a lane gives up on a slot
+#ifndef GIRIH_CUDA_EMU
+struct LLWord { unsigned lo, t0, hi, t1; };
+__device__ __forceinline__ void ll_store(void *p, double v, unsigned tag) {
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(tag), "r"(hi), "r"(tag));
+}
+__device__ __forceinline__ LLWord ll_load(const void *p) {
+  LLWord w;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.lo), "=r"(w.t0), "=r"(w.hi), "=r"(w.t1) : "l"(p));
+  return w;
+}
+__device__ __forceinline__ double ll_value(const LLWord &w) { return __hiloint2double((int)w.hi, (int)w.lo); }
+__device__ __forceinline__ LLWord ll_pack(double v, unsigned tag) {
+  LLWord w;
+  w.lo = (unsigned)__double2loint(v); w.hi = (unsigned)__double2hiint(v); w.t0 = w.t1 = tag;
+  return w;
+}
+__device__ __forceinline__ void spin_pause() { __nanosleep(100); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif   // the test suite's CPU SIMT emulator supplies its own versions (tests/cuda_emu)
+
+template <int K, typename R, int T, int PY, int NW, bool FM = false>
+__global__ void __launch_bounds__(32 * NW, 1)
+k_r1x(const R1xArgs<R> a) {
+  using Cfg = R1xCfg<R, T, PY, NW>;
+  constexpr int VX = Cfg::VX, WX = Cfg::WX, H = Cfg::H, NXS = Cfg::NXS;
+  constexpr int LEVEL_SLOTS = Cfg::LEVEL_SLOTS, RING_SLOTS = Cfg::RING_SLOTS;
+  constexpr int NCA = KTraits<K>::NCA;
+  constexpr unsigned ALL = (PY * VX >= 32) ? 0xffffffffu : ((1u << (PY * VX)) - 1u);
+  static_assert(KTraits<K>::R == 1 && KTraits<K>::TO == 1, "radius-1, first-order-in-time only");
+  static_assert(PY * VX <= 32, "point masks are 32 bits");
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // edge[l][parity][warp][0 = first row, 1 = last row][WX]; "warps" NW and NW + 1 are the rows handed over by the
+  // tiles above (y-) and below (y+)
+  R *const edge = reinterpret_cast<R *>(smem_raw);
+  auto edge_ptr = [&](int l, int par, int w, int which) GIRIH_LAMBDA_INLINE -> R * {
+    return edge + ((((size_t)l * 2 + par) * (NW + 2) + w) * 2 + which) * WX;
+  };
+  const DevGrid &g = a.g;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // xs[level][side][row]: the columns left (side 0) / right (side 1) of this warp's rows, handed over by the x neighbours
+  R *const xs = reinterpret_cast<R *>(smem_raw + Cfg::EDGE_BYTES) + (size_t)warp * (T * 2 * PY);
+
+  const int bx = (int)blockIdx.x, by = (int)blockIdx.y, cz = (int)blockIdx.z;
+  const int ni = (int)gridDim.x, nj = (int)gridDim.y;
+  const int xt0 = g.X0 + bx * WX, yt0 = g.Y0 + by * H;   // first column / row of the tile
+  const int x = xt0 + lane * VX;                          // my first column (device x)
+  const int y0 = yt0 + warp * PY;                         // my first row
+  const int zb = a.zb0 + cz * a.zchunk;
+  const int ze = min(zb + a.zchunk, a.ze0);
+  const bool has_xm = bx > 0, has_xp = bx + 1 < ni, has_ym = by > 0, has_yp = by + 1 < nj;
+  const long long cta = ((long long)cz * nj + by) * ni + bx;
+  unsigned char *const inb = a.xbuf + cta * (long long)Cfg::TILE_BYTES;   // my inbound slots
+
+  // per-point facts that do not change along z
+  const bool x_alloc = (x >= 0) && (x + VX <= g.px);
+  unsigned row_alloc = 0, interior_xy = 0;
+#pragma unroll
+  for (int j = 0; j < PY; ++j) {
+    const int y = y0 + j;
+    if (x_alloc && (y >= 0) && (y < g.ny_dev) && (y < g.Y0 + g.ny + g.r) && (x < g.X0 + g.nx + g.r)) row_alloc |= 1u << j;
+    const bool yin = (y >= g.Y0) && (y < g.Y0 + g.ny);
+#pragma unroll
+    for (int e = 0; e < VX; ++e) {
+      const bool xin = (x + e >= g.X0) && (x + e < g.X0 + g.nx);
+      if (xin && yin) interior_xy |= 1u << (j * VX + e);
+    }
+  }
+  const bool warp_masked = __any_sync(0xffffffffu, interior_xy != ALL);
+  unsigned full_rows = 0, part_rows = 0;   // rows stored whole / point by point (every interior point is stored)
+#pragma unroll
+  for (int j = 0; j < PY; ++j) {
+    const unsigned m = (interior_xy >> (j * VX)) & ((1u << VX) - 1u);
+    if (m == (1u << VX) - 1u) full_rows |= 1u << j;
+    else if (m != 0u) part_rows |= 1u << j;
+  }
+  const bool any_part = __any_sync(0xffffffffu, part_rows != 0u);
+  const long long row0 = (long long)y0 * g.px + x;
+  const R *const coef_t = a.coef + row0;
+  const int nit = (ze - zb) + 2 * T;
+
+  // ---- publishing: where my rim values go -------------------------------------------------------------
+  // lane 0 hands its first column to the left tile (its x+ slots), lane 31 its last column to the right tile (x- slots)
+  unsigned char *xpub = nullptr;
+  if (lane == 0 && has_xm) xpub = inb - (long long)Cfg::TILE_BYTES + (size_t)(H + warp * PY) * 16;
+  if (lane == 31 && has_xp) xpub = inb + (long long)Cfg::TILE_BYTES + (size_t)(warp * PY) * 16;
+  // warp 0 hands its first row to the tile above (its y+ slots), warp NW-1 its last row to the tile below (y- slots)
+  unsigned char *ypub = nullptr;
+  if (warp == 0 && has_ym) ypub = inb - (long long)ni * (long long)Cfg::TILE_BYTES + (size_t)(2 * H + WX + lane * VX) * 16;
+  if (warp == NW - 1 && has_yp) ypub = inb + (long long)ni * (long long)Cfg::TILE_BYTES + (size_t)(2 * H + lane * VX) * 16;
+  const bool edge_warp = (warp == 0) || (warp == NW - 1);
+
+  // ---- polling: the slots each lane collects ----------------------------------------------------------------
+  // A rim value of level l is published in iteration g (when the stage that produces level l ends; level 0: at the top)
+  // and consumed by stage l of iteration g + 1.  Every value is collected as LATE as possible, in the stage before the
+  // one that consumes it: stage s of iteration `it` polls level s + 1 of iteration it - 1 (s < T - 1), stage T - 1 polls
+  // level 0 of iteration `it`.  That leaves T - 1 stages (~1700 cycles at T = 4) between a store and the first look at
+  // its slot, against a measured hand-over latency of 700 (same die) .. 1050 (other die) cycles
+  // (tools/micro/ll_pingpong.cu), so a poll normally succeeds at once.  Everything is private to the consuming warp:
+  //   x: lanes < NXS of every warp collect the warp's 2 * PY column values (one slot each) into xs[]
+  //   y: the first / last warp collects the row above / below the tile, 2 slots per lane, into the edge rows
+  // kinds: 0 none, 1 slot written by a neighbour tile, 2 Dirichlet frame cell read from the input array
+  int kX = 0, kY = 0;
+  unsigned sX = 0, sY = 0;   // slot byte offset inside one (ring, level 0) block -- or in-plane element offset (kind 2)
+  int dX = 0, dY = 0;        // destination: xs index (level 0) / edge-row element offset (level 0, parity 0)
+  if (lane < NXS) {
+    const int side = lane / PY, j = lane % PY;
+    const bool has = side == 0 ? has_xm : has_xp;
+    dX = side * PY + j;
+    if (has) { kX = 1; sX = (unsigned)((side * H + warp * PY + j) * 16); }
+    else {
+      const int xc = side == 0 ? xt0 - 1 : xt0 + WX, yr = y0 + j;
+      kX = (xc >= 0 && xc < g.px && yr >= 0 && yr < g.ny_dev) ? 2 : 0;
+      sX = (unsigned)(yr * g.px + xc);
+    }
+  }
+  if (edge_warp) {
+    const int side = warp == 0 ? 0 : 1;
+    const bool has = side == 0 ? has_ym : has_yp;
+    dY = (int)(edge_ptr(0, 0, NW + side, side == 0 ? 1 : 0) - edge) + lane * VX;
+    if (has) { kY = 1; sY = (unsigned)((2 * H + side * WX + lane * VX) * 16); }
+    else {
+      const int yr = side == 0 ? yt0 - 1 : yt0 + H;
+      kY = (yr >= 0 && yr < g.ny_dev && x_alloc) ? 2 : 0;
+      sY = (unsigned)(yr * g.px + x);
+    }
+  }
+  constexpr int EDGE_PAR = (NW + 2) * 2 * WX;        // elements between the two parities of one level's edge rows
+  constexpr int EDGE_LVL = 2 * EDGE_PAR;             // ... between levels
+
+  {
+  R S[T][3][PY][VX];
+#pragma unroll
+  for (int l = 0; l < T; ++l)
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int j = 0; j < PY; ++j)
+#pragma unroll
+        for (int e = 0; e < VX; ++e) S[l][q][j][e] = (R)0;
+
+  auto load_plane = [&](int z, R (&dst)[PY][VX], bool want = true) {
+    const unsigned m = (want && (z >= 0) && (z < g.nz_dev)) ? row_alloc : 0u;
+    const R *p = a.in + (long long)z * g.pxy + row0;
+#pragma unroll
+    for (int j = 0; j < PY; ++j)
+      if ((m >> j) & 1u) ld128<R>(p + (long long)j * g.px, dst[j]);
+  };
+  load_plane(zb - T, S[0][2]);   // "F" of phase 0
+
+  // one slot: issue() starts the load, finish() spins until the tag of the wanted iteration is there.  A frame cell
+  // (kind 2) is read from plane zp of the input array and wrapped so that finish() accepts it at once.
+  auto issue = [&](int kind, const unsigned char *slot, unsigned off, int zp, unsigned tag) GIRIH_LAMBDA_INLINE -> LLWord {
+    LLWord w;
+    w.lo = w.hi = 0u; w.t0 = w.t1 = tag;
+    if (kind == 1) w = ll_load(slot);
+    else if (kind == 2 && zp >= 0 && zp < g.nz_dev) {
+      const R *q = a.in + (long long)zp * g.pxy + off;
+      w = ll_pack(__ldg(q), tag);
+      if (zp + 2 < g.nz_dev) prefetch_l2(q + 2 * g.pxy);   // the same cell two planes on: wanted two iterations from now
+    }
+    return w;
+  };
+  bool gave_up = false;   // after one time-out this lane no longer waits: the launch ends quickly and the host sees *err
+  auto finish = [&](int kind, const unsigned char *slot, LLWord w, unsigned tag) GIRIH_LAMBDA_INLINE -> R {
+    if (kind == 1) {
+      unsigned spins = 0;
+      while ((w.t0 != tag || w.t1 != tag) && !gave_up) {
+        if (++spins > R1X_SPIN_LIMIT) { gave_up = true; *a.err = 1; break; }
+        spin_pause();   // a short sleep: a warp that re-polls at once floods the slot's L2 line and delays the store it waits for
+        w = ll_load(slot);
+      }
+    }
+    return ll_value(w);
+  };
+
+  auto body = [&](auto phase_tag, auto frame_tag, const int it) GIRIH_LAMBDA_INLINE {
+    constexpr int PH = decltype(phase_tag)::value;
+    constexpr bool FRAME = decltype(frame_tag)::value;
+    constexpr int iB = PH, iC = (PH + 1) % 3, iF = (PH + 2) % 3;
+    constexpr int RING_CUR = PH, RING_PREV = (PH + 2) % 3;      // ring slot of iteration it / it - 1 (it % 3 == PH)
+    const int zin = zb - T + it;
+    const int cur = it & 1;
+    const unsigned tag = a.seq0 + (unsigned)it + 1u;           // this iteration's tag; the previous one is tag - 1
+
+    auto publish = [&](auto level_tag, const R (&P)[PY][VX]) {
+      // rim of the newest plane of level l: to the other warps through shared memory, to the other tiles through L2
+      constexpr int l = decltype(level_tag)::value;
+      st128<R>(edge_ptr(l, cur, warp, 0) + lane * VX, P[0]);
+      st128<R>(edge_ptr(l, cur, warp, 1) + lane * VX, P[PY - 1]);
+      constexpr size_t off = (size_t)(RING_CUR * RING_SLOTS + l * LEVEL_SLOTS) * 16;
+      if (xpub != nullptr) {
+#pragma unroll
+        for (int j = 0; j < PY; ++j) ll_store(xpub + off + (size_t)j * 16, lane == 0 ? P[j][0] : P[j][VX - 1], tag);
+      }
+      if (ypub != nullptr) {   // warp-uniform
+        if (warp == 0) {
+#pragma unroll
+          for (int e = 0; e < VX; ++e) ll_store(ypub + off + (size_t)e * 16, P[0][e], tag);
+        } else {
+#pragma unroll
+          for (int e = 0; e < VX; ++e) ll_store(ypub + off + (size_t)e * 16, P[PY - 1][e], tag);
+        }
+      }
+    };
+
+    publish(Level<0>{}, S[0][iF]);
+
+    R Ofin[PY][VX];
+    auto level = [&](auto level_tag) GIRIH_LAMBDA_INLINE {
+      constexpr int l = decltype(level_tag)::value;
+      const int zc = zin - l - 1;
+      R (&Bp)[PY][VX] = S[l][iB];
+      R (&Cp)[PY][VX] = S[l][iC];
+      R (&Fp)[PY][VX] = S[l][iF];
+
+      // ---- this stage's poll round: issue now, finish after the arithmetic (see "polling" above) ---------------
+      constexpr int lv = (l + 1) % T;                       // level collected in this stage
+      constexpr bool PREV = (l + 1 < T);                    // ... of the previous iteration (else: level 0 of this one)
+      constexpr int RING_P = PREV ? RING_PREV : RING_CUR;
+      const unsigned ptag = PREV ? tag - 1u : tag;
+      const int zp = PREV ? zin - 1 - lv : zin;             // plane of that level's newest values
+      const bool pactive = !PREV || it > 0;
+      const unsigned char *const px0 = inb + (size_t)(RING_P * RING_SLOTS + lv * LEVEL_SLOTS) * 16 + sX;
+      const unsigned char *const py0 = inb + (size_t)(RING_P * RING_SLOTS + lv * LEVEL_SLOTS) * 16 + sY;
+      const int kx = pactive ? kX : 0, ky = (pactive && edge_warp) ? kY : 0;
+      LLWord wx = issue(kx, px0, sX, zp, ptag);
+      LLWord wy0, wy1;
+      wy0.lo = wy0.hi = 0u; wy0.t0 = wy0.t1 = ptag;
+      wy1 = wy0;
+      if (edge_warp) {   // warp-uniform
+        wy0 = issue(ky, py0, sY, zp, ptag);
+        wy1 = issue(ky, py0 + 16, sY + 1u, zp, ptag);
+      }
+
+      // rows just outside my strip: neighbouring warps, or (first / last warp) the neighbouring tiles
+      R up[VX], dn[VX];
+      {
+        const int wu = (warp > 0) ? warp - 1 : NW, wd = (warp < NW - 1) ? warp + 1 : NW + 1;
+        ld128s<R>(edge_ptr(l, cur ^ 1, wu, 1) + lane * VX, up);
+        ld128s<R>(edge_ptr(l, cur ^ 1, wd, 0) + lane * VX, dn);
+      }
+      // columns just outside my span: lane 0 takes the left one, lane 31 the right one
+      const R *const xq = xs + (l * 2 + (lane == 31 ? 1 : 0)) * PY;
+
+      auto stage = [&](R (&O)[PY][VX]) {
+#pragma unroll
+        for (int j = 0; j < PY; ++j) {
+          R cf[NCA > 0 ? NCA : 1][VX];
+          if constexpr (NCA > 0) {
+            const bool ok = (zc >= 0) && (zc < g.nz_dev) && ((row_alloc >> j) & 1u);
+            const R *cp = coef_t + ((long long)zc * g.pxy + (long long)j * g.px);
+#pragma unroll
+            for (int m = 0; m < NCA; ++m) {
+#pragma unroll
+              for (int e = 0; e < VX; ++e) cf[m][e] = (R)0;
+              if (ok) ld128<R>(cp + (long long)m * a.coef_stride, cf[m]);
+            }
+          }
+          R left = __shfl_up_sync(0xffffffffu, Cp[j][VX - 1], 1);
+          R right = __shfl_down_sync(0xffffffffu, Cp[j][0], 1);
+          const R xvj = xq[j];
+          left = (lane == 0) ? xvj : left;
+          right = (lane == 31) ? xvj : right;
+#pragma unroll
+          for (int e = 0; e < VX; ++e) {
+            RegNb1<R> n;
+            n.c = Cp[j][e];
+            n.xm = (e > 0) ? Cp[j][e > 0 ? e - 1 : 0] : left;
+            n.xp = (e < VX - 1) ? Cp[j][e < VX - 1 ? e + 1 : 0] : right;
+            n.ym = (j > 0) ? Cp[j > 0 ? j - 1 : 0][e] : up[e];
+            n.yp = (j < PY - 1) ? Cp[j < PY - 1 ? j + 1 : 0][e] : dn[e];
+            n.zm = Bp[j][e];
+            n.zp = Fp[j][e];
+            if constexpr (NCA > 0) {
+              RegCoef<R, NCA> rc;
+#pragma unroll
+              for (int m = 0; m < NCA; ++m) rc.v[m] = cf[m][e];
+              O[j][e] = StencilExpr<K>::template eval<R, FM>(n, rc, (R)0, (R)0);
+            } else {
+              O[j][e] = StencilExpr<K>::template eval<R, FM>(n, a.cc, (R)0, (R)0);
+            }
+          }
+        }
+        if constexpr (FRAME) {
+          const unsigned upd = ((zc >= g.zlo) && (zc < g.zhi)) ? interior_xy : 0u;
+#pragma unroll
+          for (int j = 0; j < PY; ++j)
+#pragma unroll
+            for (int e = 0; e < VX; ++e) O[j][e] = ((upd >> (j * VX + e)) & 1u) ? O[j][e] : Cp[j][e];
+        }
+        if constexpr (l + 1 < T) publish(Level<l + 1>{}, O);
+      };
+      if constexpr (l + 1 < T) stage(S[l + 1][iF]);
+      else stage(Ofin);
+      if constexpr (l == 0) load_plane(zin + 1, S[0][iB], it + 1 < nit);
+
+      // ---- finish this stage's poll round: payloads into shared memory, for the next stage of this warp --------
+#ifdef GIRIH_R1X_TRACE
+      const bool tr = a.trace != nullptr && lane == 0 && (warp == 0 || warp == 3) && it >= 96 && it < 112;
+      long long *const trp = a.trace + ((((cta * 2 + (warp == 0 ? 0 : 1)) * 16 + (it - 96)) * T + l) * 2);
+      if (tr) trp[0] = clock64();
+#endif
+      if (kx != 0) xs[lv * 2 * PY + dX] = finish(kx, px0, wx, ptag);
+      if (edge_warp) {
+        if (ky != 0) {
+          R t[VX];
+          t[0] = finish(ky, py0, wy0, ptag);
+          t[1] = finish(ky, py0 + 16, wy1, ptag);
+          // consumed through parity cur ^ 1 of the iteration that reads it: this one (PREV) or the next one
+          st128<R>(edge + dY + lv * EDGE_LVL + (PREV ? (cur ^ 1) : cur) * EDGE_PAR, t);
+        }
+      }
+      __syncwarp();
+#ifdef GIRIH_R1X_TRACE
+      if (tr) trp[1] = clock64();
+#endif
+    };
+    static_for<0, T>(level);
+
+    // Ofin is level T at plane zin - T: every interior point of the tile is stored
+    {
+      const int zo = zin - T;
+      const bool zst = (zo >= zb) && (zo < ze);
+      R *q = a.out + (long long)zo * g.pxy + row0;
+      const unsigned fm = zst ? full_rows : 0u;
+#pragma unroll
+      for (int j = 0; j < PY; ++j)
+        if ((fm >> j) & 1u) st128<R>(q + (long long)j * g.px, Ofin[j]);
+      if (any_part && zst) {
+#pragma unroll
+        for (int j = 0; j < PY; ++j) {
+          if ((part_rows >> j) & 1u) {
+            const unsigned m = (interior_xy >> (j * VX)) & ((1u << VX) - 1u);
+#pragma unroll
+            for (int e = 0; e < VX; ++e)
+              if ((m >> e) & 1u) q[(long long)j * g.px + e] = Ofin[j][e];
+          }
+        }
+      }
+    }
+    __syncthreads();
+  };
+
+  auto step = [&](auto phase_tag, const int it) GIRIH_LAMBDA_INLINE {
+    const int zin = zb - T + it;
+    if (warp_masked || (zin - T < g.zlo) || (zin > g.zhi)) body(phase_tag, FrameTag<true>{}, it);
+    else body(phase_tag, FrameTag<false>{}, it);
+  };
+  int it = 0;
+  for (; it + 3 <= nit; it += 3) {
+    step(Phase<0>{}, it);
+    step(Phase<1>{}, it + 1);
+    step(Phase<2>{}, it + 2);
+  }
+  if (it < nit) { step(Phase<0>{}, it); ++it; }
+  if (it < nit) { step(Phase<1>{}, it); }
+  }
+}
+
+}  // namespace girih

@@ -12,6 +12,19 @@
 #define GIRIH_LAUNCH(kfn, grid, block, smem, stream, ...) (kfn)<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
+// Cooperative launch (all CTAs of the grid co-resident): the exact-tiled sweep (kernels_r1x.cuh), whose CTAs wait for
+// each other's rim values.  `arg` is the kernel's single by-value argument struct.
+#ifndef GIRIH_LAUNCH_COOP
+#define GIRIH_LAUNCH_COOP(kfn, grid, block, smem, stream, arg) \
+  girih::launch_cooperative((const void *)(kfn), (grid), (block), (smem), (stream), (void *)&(arg))
+namespace girih {
+static inline cudaError_t launch_cooperative(const void *f, dim3 grid, dim3 block, size_t smem, cudaStream_t s, void *arg) {
+  void *args[1] = {arg};
+  return cudaLaunchCooperativeKernel(f, grid, block, args, smem, s);
+}
+}  // namespace girih
+#endif
+
 namespace girih {
 
 struct StreamLaunch {
@@ -32,8 +45,18 @@ struct StreamLaunch {
   // nullptr / empty plane ranges when the pass pushes nothing
   void *push_up = nullptr, *push_dn = nullptr;
   int push_up_from = 0x7fffffff, push_dn_below = -0x7fffffff;
+  // exact-tiled sweep (kernels_r1x.cuh): inbound edge slots of the context, the running slot tag, the give-up flag, and
+  // how many CTAs the device keeps resident at once.  nullptr = the context has none: overlapped tiles only
+  unsigned char *xbuf = nullptr;
+  size_t xbuf_bytes = 0;
+  unsigned *xseq = nullptr;
+  int *xerr = nullptr;
+  int nsm = 148;
   cudaStream_t stream;
 };
+
+// is `tile` one of the exact-tiled (non-overlapping, edge hand-off) variants?  10000 + PY*100 + NW
+static inline bool tile_is_exact(int tile) { return tile >= 10000 && tile < 20000; }
 
 // T fused steps of a radius-1 operator (slots 1, 2, 3, 5); es = sizeof(real)
 cudaError_t launch_r1(int kernel, int es, int T, const StreamLaunch &a);

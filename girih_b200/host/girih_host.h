@@ -63,6 +63,7 @@ typedef struct Parameters {
   int gpu_variant;                  /* --gpu-variant: 0 auto, 1 naive kernels */
   int gpu_overlap;                  /* --gpu-overlap: overlap halo exchange with compute */
   int gpu_push;                     /* --gpu-push: fused passes store boundary planes into the neighbours' halos (peer memory) */
+  int gpu_copy;                     /* --gpu-copy: overlapped passes, halos moved into the neighbours' halo planes by the copy engines */
   int gpu_tune;                     /* --gpu-tune: on-device search over fusion depth and tiles ([AUTO TUNE]) */
   int gpu_contract;                 /* --gpu-contract: FMA-contracted arithmetic (reference built with -mfma) */
   /* decomposition */

@@ -322,7 +322,7 @@ void gpu_attach(Parameters *p) {
   }
   gpu_check(p, girih_gpu_set_option(p->gpu, "variant", p->gpu_variant), "girih_gpu_set_option");
   gpu_check(p, girih_gpu_set_option(p->gpu, "overlap", p->gpu_overlap), "girih_gpu_set_option");
-  if (p->gpu_push && p->mpi_size > 1 && p->t.shape[0] == 1 && p->t.shape[1] == 1) {
+  if ((p->gpu_push || p->gpu_copy) && p->mpi_size > 1 && p->t.shape[0] == 1 && p->t.shape[1] == 1) {
     /* every rank thread maps its z neighbours' arrays (one process: peer access) */
     unsigned char mine[GIRIH_PEER_BLOB_BYTES];
     unsigned char *all = (unsigned char *)malloc((size_t)p->mpi_size * GIRIH_PEER_BLOB_BYTES);
@@ -333,7 +333,7 @@ void gpu_attach(Parameters *p) {
     if (p->mpi_rank + 1 < p->mpi_size)
       gpu_check(p, girih_gpu_peer_attach(p->gpu, 1, all + (size_t)(p->mpi_rank + 1) * GIRIH_PEER_BLOB_BYTES, GIRIH_PEER_BLOB_BYTES), "girih_gpu_peer_attach");
     free(all);
-    gpu_check(p, girih_gpu_set_option(p->gpu, "halo_push", 1), "girih_gpu_set_option");
+    gpu_check(p, girih_gpu_set_option(p->gpu, p->gpu_copy ? "halo_copy" : "halo_push", 1), "girih_gpu_set_option");
   }
   gpu_check(p, girih_gpu_set_option(p->gpu, "contract", p->gpu_contract), "girih_gpu_set_option");
   gpu_check(p, girih_gpu_upload(p->gpu, p->U1, p->U2, p->U3, p->coef), "girih_gpu_upload");

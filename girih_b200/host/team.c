@@ -7,6 +7,7 @@
  */
 #define _GNU_SOURCE
 #include <pthread.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -52,7 +53,10 @@ void team_reduce(const double *in, double *max, double *min, double *sum, int n,
 
 void team_bcast(void *buf, size_t len, int root, int rank) {
   if (T.n == 1) return;
-  if (len > sizeof(T.bcast)) len = sizeof(T.bcast);
+  if (len > sizeof(T.bcast)) {   /* never truncate silently: the receivers would act on a partial message */
+    fprintf(stderr, "ERROR: team_bcast of %zu bytes exceeds the %zu-byte slot\n", len, sizeof(T.bcast));
+    exit(1);
+  }
   if (rank == root) memcpy(T.bcast, buf, len);
   team_barrier();
   if (rank != root) memcpy(buf, T.bcast, len);
@@ -62,7 +66,10 @@ void team_bcast(void *buf, size_t len, int root, int rank) {
 void team_allgather(const void *mine, size_t len, void *all, int rank) {
   static unsigned char slots[64][256];
   int r;
-  if (len > 256 || T.n > 64) return;
+  if (len > 256 || T.n > 64) {   /* the callers size `all` for T.n * len bytes and read all of it */
+    fprintf(stderr, "ERROR: team_allgather: %zu bytes x %d ranks exceed the 256-byte x 64-rank slots\n", len, T.n);
+    exit(1);
+  }
   memcpy(slots[rank], mine, len);
   team_barrier();
   for (r = 0; r < T.n; r++) memcpy((unsigned char *)all + (size_t)r * len, slots[r], len);

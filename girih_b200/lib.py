@@ -16,7 +16,7 @@ ABI_SYMBOLS = [
     "girih_gpu_comm_unique_id", "girih_gpu_comm_init", "girih_gpu_set_topology", "girih_gpu_peer_export", "girih_gpu_peer_attach", "girih_gpu_peer_detach", "girih_gpu_upload", "girih_gpu_download",
     "girih_gpu_upload_fields", "girih_gpu_prefetch_fields", "girih_gpu_commit_fields", "girih_gpu_download_async",
     "girih_gpu_sync_transfers", "girih_gpu_run_single", "girih_gpu_run_fused", "girih_gpu_step_box",
-    "girih_gpu_time_pass", "girih_gpu_last_elapsed_ms", "girih_gpu_last_launch_info", "girih_gpu_scan_u1", "girih_gpu_set_option",
+    "girih_gpu_time_pass", "girih_gpu_last_elapsed_ms", "girih_gpu_last_launch_info", "girih_gpu_get_stat", "girih_gpu_scan_u1", "girih_gpu_set_option",
     "girih_gpu_autotune",
     "girih_gpu_strerror", "girih_gpu_last_error", "girih_plan_fused_passes", "girih_plan_halo_exchange", "girih_plan_fused_exchanges",
 ]
@@ -70,6 +70,7 @@ def declare(lib: C.CDLL) -> C.CDLL:
     lib.girih_gpu_time_pass.argtypes = [P, I, I, C.POINTER(C.c_double)]
     lib.girih_gpu_last_elapsed_ms.argtypes = [P] + [C.POINTER(C.c_double)] * 3
     lib.girih_gpu_last_launch_info.argtypes = [P] + [C.POINTER(I)] * 4
+    lib.girih_gpu_get_stat.argtypes = [P, C.c_char_p, C.POINTER(C.c_longlong)]
     lib.girih_gpu_scan_u1.argtypes = [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.girih_gpu_set_option.argtypes = [P, C.c_char_p, I]
     lib.girih_gpu_autotune.argtypes = [P, I, I, C.POINTER(I), C.POINTER(I), C.POINTER(C.c_double)]

@@ -204,6 +204,10 @@ int girih_gpu_last_elapsed_ms(girih_gpu_ctx *ctx, double *compute_ms, double *co
 /* Launch accounting of the last run_* call: kernels launched, fused passes, steps executed. */
 int girih_gpu_last_launch_info(girih_gpu_ctx *ctx, int *n_kernels, int *n_passes, int *n_steps,
                                int *tfuse_used);
+/* Named counters of the context (since creation): "exact_launches" = fused passes that ran on exact (non-overlapping)
+ * tiles with edge hand-off between co-resident CTAs, the GPU form of the reference's non-redundant diamond tiles
+ * (src/kernels/diamond_ts.c:565-595); "fused_launches" = all fused passes.  GIRIH_ERR_ARG for an unknown key. */
+int girih_gpu_get_stat(girih_gpu_ctx *ctx, const char *key, long long *value);
 
 /* Measurement hook for the roofline figure: launches `reps` passes of `tfuse` fused steps back to
  * back over the whole slab (ping-ponging U1/U2, so the fields keep evolving) and returns the

@@ -165,7 +165,7 @@ def compare(ref_full, target_interior, stencil, r):
 # ----------------------------------------------------------------------------------------------
 # the real reference (oracle/_ref), when present
 # ----------------------------------------------------------------------------------------------
-def ref_dump(kernel, stencil, nt, dtype=np.float64, ts=0, extra=(), threads=2, fast=False):
+def ref_dump(kernel, stencil, nt, dtype=np.float64, ts=0, extra=(), threads=2, fast=False, timeout=600):
     """Run the unmodified reference stepper and return (U1 full domain [z,y,x], r, nt_effective).
     fast=True uses the build with FMA contraction (-O3 -mfma -ffp-contract=fast)."""
     exe = os.path.join(REF_DIR, "ref_dump_" + _sfx(dtype) + ("_fast" if fast else ""))
@@ -179,7 +179,7 @@ def ref_dump(kernel, stencil, nt, dtype=np.float64, ts=0, extra=(), threads=2, f
         if ts != 2:
             cmd += ["--thread-group-size", str(threads)]
         cmd += [str(e) for e in extra]
-        subprocess.run(cmd, env=env, check=True, stdout=subprocess.DEVNULL, timeout=600)
+        subprocess.run(cmd, env=env, check=True, stdout=subprocess.DEVNULL, timeout=timeout)
         raw = open(path, "rb").read()
     finally:
         os.unlink(path)

@@ -11,7 +11,12 @@
 #include <omp.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <sched.h>
 #include <sys/mman.h>
+#include <time.h>
+
+#include <thread>
+#include <vector>
 
 namespace girih {
 __thread __attribute__((aligned(128))) unsigned char smem_raw[cuda_emu::SMEM_BYTES];
@@ -263,6 +268,45 @@ void launch_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()>
     uint3 bid{(unsigned)(i % grid.x), (unsigned)((i / grid.x) % grid.y), (unsigned)(i / ((long)grid.x * grid.y))};
     run_block(bid, grid, block, entry);
   }
+}
+
+// Cooperative launch: one OS thread per CTA, all running at once -- CTAs of kernels_r1x.cuh poll slots that other CTAs
+// fill.  A fiber that spins on another CTA calls coop_pause(): the other fibers of its CTA get their turn, then the OS
+// scheduler; the per-CTA deadlock counter does not apply (progress comes from outside), a wall-clock limit does.
+static thread_local double coop_t0 = 0;
+static double now_s() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+void coop_pause() {
+  Block *b = B;
+  b->idle = 0;
+  if (coop_t0 == 0) coop_t0 = now_s();
+  else if (now_s() - coop_t0 > 300.0) die("cooperative launch: a CTA waited 300 s for another CTA");
+  yield();
+  sched_yield();
+}
+
+void launch_coop_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()> &entry) {
+  const long nthr = (long)block.x * block.y * block.z;
+  const long nblocks = (long)grid.x * grid.y * grid.z;
+  if (nthr < 1 || nthr > 1024 || smem > SMEM_BYTES || nblocks < 1 || nblocks > 148) {
+    last_error = nblocks > 148 ? cudaErrorCooperativeLaunchTooLarge : cudaErrorInvalidValue;
+    return;
+  }
+  const char *e = getenv("CUDA_EMU_SCHED");
+  g_sched = e ? atoi(e) : 0;
+  std::vector<std::thread> th;
+  th.reserve((size_t)nblocks);
+  for (long i = 0; i < nblocks; ++i)
+    th.emplace_back([=, &entry]() {
+      rng_state = 0x9e3779b97f4a7c15ull ^ (unsigned long long)(i * 0x2545F4914F6CDD1Dull + 1);
+      coop_t0 = 0;
+      uint3 bid{(unsigned)(i % grid.x), (unsigned)((i / grid.x) % grid.y), (unsigned)(i / ((long)grid.x * grid.y))};
+      run_block(bid, grid, block, entry);
+    });
+  for (auto &t : th) t.join();
 }
 
 }  // namespace cuda_emu

@@ -38,7 +38,8 @@ static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorLaunchFailure = 719 };
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorLaunchFailure = 719, cudaErrorCooperativeLaunchTooLarge = 720,
+       cudaErrorNotSupported = 801 };
 typedef void *cudaStream_t;
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaDevAttrMultiProcessorCount = 16 };
 
@@ -84,6 +85,9 @@ void yield();
 void syncthreads();
 unsigned long long warp_exchange(unsigned long long v, int src_lane);   // every lane deposits, reads src_lane
 void launch_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()> &entry);
+// cooperative launch: every CTA of the grid runs at the same time (one OS thread per CTA), so CTAs may wait for each other
+void launch_coop_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()> &entry);
+void coop_pause();   // inside a spin on another CTA's progress: lets the other fibers of this CTA and the other CTAs run
 void cp_async_issue(void *dst, const void *src);
 void cp_async_commit_group();
 void cp_async_wait_group(int n);
@@ -92,6 +96,15 @@ template <typename F, typename... A>
 static inline void launch(F kfn, dim3 grid, dim3 block, size_t smem, cudaStream_t, A... args) {
   std::function<void()> entry = [=]() { kfn(args...); };
   launch_impl(grid, block, smem, entry);
+}
+
+template <typename F, typename A>
+static inline cudaError_t launch_coop(F kfn, dim3 grid, dim3 block, size_t smem, cudaStream_t, A arg) {
+  std::function<void()> entry = [=]() { kfn(arg); };
+  launch_coop_impl(grid, block, smem, entry);
+  const int e = last_error;
+  last_error = 0;
+  return e;
 }
 
 template <typename T> static inline unsigned long long to_bits(T v) {
@@ -110,6 +123,8 @@ template <typename T> static inline T from_bits(unsigned long long b) {
 
 #define GIRIH_LAUNCH(kfn, grid, block, smem, stream, ...) \
   cuda_emu::launch((kfn), dim3(grid), dim3(block), (size_t)(smem), (stream), __VA_ARGS__)
+#define GIRIH_LAUNCH_COOP(kfn, grid, block, smem, stream, arg) \
+  cuda_emu::launch_coop((kfn), dim3(grid), dim3(block), (size_t)(smem), (stream), (arg))
 
 #define threadIdx (cuda_emu::TH->tid)
 #define blockIdx (cuda_emu::B->bid)
@@ -117,6 +132,9 @@ template <typename T> static inline T from_bits(unsigned long long b) {
 #define gridDim (cuda_emu::B->gdim)
 
 static inline void __syncthreads() { cuda_emu::syncthreads(); }
+// the lanes of a warp are fibers of one OS thread: a fiber switch orders their memory accesses.  One empty warp
+// collective makes __syncwarp a real meeting point (a lane that runs ahead would otherwise read stale scratch).
+static inline void __syncwarp() { (void)cuda_emu::warp_exchange(0ull, cuda_emu::TH->lane); }
 
 // full-mask warp primitives (the only form the kernels use)
 template <typename T> static inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
@@ -233,6 +251,33 @@ static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long 
 
 // cp.async wrappers of kernels_r4.cuh and the split barrier of kernels_r1.cuh (the product versions are inline PTX)
 namespace girih {
+// LL slots of kernels_r1x.cuh: two 8-byte words {payload half, tag}, each written / read atomically
+struct LLWord { unsigned lo, t0, hi, t1; };
+static inline void ll_store(void *p, double v, unsigned tag) {
+  unsigned long long b;
+  memcpy(&b, &v, 8);
+  unsigned long long *q = (unsigned long long *)p;
+  __atomic_store_n(q, (b & 0xffffffffull) | ((unsigned long long)tag << 32), __ATOMIC_SEQ_CST);
+  __atomic_store_n(q + 1, (b >> 32) | ((unsigned long long)tag << 32), __ATOMIC_SEQ_CST);
+}
+static inline LLWord ll_load(const void *p) {
+  const unsigned long long *q = (const unsigned long long *)p;
+  const unsigned long long w0 = __atomic_load_n(q, __ATOMIC_SEQ_CST), w1 = __atomic_load_n(q + 1, __ATOMIC_SEQ_CST);
+  return LLWord{(unsigned)w0, (unsigned)(w0 >> 32), (unsigned)w1, (unsigned)(w1 >> 32)};
+}
+static inline double ll_value(const LLWord &w) {
+  const unsigned long long b = (unsigned long long)w.lo | ((unsigned long long)w.hi << 32);
+  double v;
+  memcpy(&v, &b, 8);
+  return v;
+}
+static inline LLWord ll_pack(double v, unsigned tag) {
+  unsigned long long b;
+  memcpy(&b, &v, 8);
+  return LLWord{(unsigned)b, tag, (unsigned)(b >> 32), tag};
+}
+static inline void spin_pause() { cuda_emu::coop_pause(); }
+static inline void prefetch_l2(const void *) {}
 // mbarrier word: [phase:32][expected:16][pending:16]; all fibers of a CTA run on one OS thread
 static inline void sb_init(unsigned long long *bar, int count) { *bar = ((unsigned long long)count << 16) | (unsigned)count; }
 static inline void sb_arrive(unsigned long long *bar) {

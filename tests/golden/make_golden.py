@@ -13,6 +13,11 @@ interior of p.U1 is stored:
 The reference ships no golden vectors of its own; these are outputs of the
 reference itself, which is what its --verify mode compares against bit for bit.
 
+`python tests/golden/make_golden.py baseline` writes checksums_baseline.json: sha256 of the reference's output at
+the sizes BASELINE.json's configs name (C1 256^3 x 100 with both steppers, C2 512^3 x 500 Diamond = the bench workload
+itself, C3 768^3 x 200 25-point, C4 512^3 x 200 per-point coefficients), fp64, so that the GPU parity suite compares
+the full-size runs with the reference and not with itself.  Takes several minutes of CPU time.
+
 `python tests/golden/make_golden.py fma` writes small_fma.npz / checksums_fma.json instead: the same
 cases run by the reference built with FMA contraction (oracle/_ref/ref_dump_*_fast, gcc -O3 -mfma
 -ffp-contract=fast) -- the fixtures for the library's "contract" option.
@@ -44,6 +49,38 @@ LARGE = [(k, (64, 48, 40), 32, 0, 0) for k in (0, 1, 2, 3, 4, 5)] + [
     (0, (96, 96, 96), 40, 0, 0),
     (4, (72, 72, 72), 20, 0, 0),
 ]
+
+
+# BASELINE.json configs at full size (fp64): (kernel, stencil, nt, ts, t_dim)
+BASELINE = [
+    (1, (256, 256, 256), 100, 0, 0),      # C1, spatial blocking
+    (1, (256, 256, 256), 100, 2, 7),      # C1, Diamond (README flags: t_dim 7 -> nt 114)
+    (1, (512, 512, 512), 500, 2, 7),      # C2 = bench.py's workload (nt 514, 513 steps)
+    (0, (768, 768, 768), 200, 2, 1),      # C3, 25-point constant coefficients (Diamond t_dim 1 -> nt 202)
+    (2, (512, 512, 512), 200, 2, 3),      # C4, 7-point variable coefficients
+    (5, (512, 512, 512), 200, 2, 3),      # C4, 7-point variable coefficients without symmetry
+]
+
+
+def main_baseline():
+    import time
+    assert O.have_ref(), "build the reference first: make -C oracle ref"
+    path = os.path.join(HERE, "checksums_baseline.json")
+    sums = json.load(open(path)) if os.path.exists(path) else {}
+    nthr = len(os.sched_getaffinity(0))
+    for (k, st, nt, ts, td) in BASELINE:
+        kk = key(k, st, nt, ts, td, "dp")
+        if kk in sums:
+            continue
+        t0 = time.time()
+        U1, r, nte = O.ref_dump(k, st, nt, np.float64, ts, ts_extra(ts, td), threads=nthr, timeout=7200)
+        nx, ny, nz = st
+        it = np.ascontiguousarray(U1[r:r + nz, r:r + ny, r:r + nx])
+        sums[kk] = {"sha256": hashlib.sha256(it.tobytes()).hexdigest(), "nt_effective": nte,
+                    "max_abs": float(np.abs(it[np.isfinite(it)]).max()), "n_nonfinite": int((~np.isfinite(it)).sum())}
+        print(kk, sums[kk], f"{time.time() - t0:.0f} s", flush=True)
+        with open(path, "w") as f:
+            json.dump(sums, f, indent=1, sort_keys=True)
 
 
 def ts_extra(ts, t_dim):
@@ -80,4 +117,7 @@ def main(fast=False):
 
 
 if __name__ == "__main__":
-    main(fast=(len(sys.argv) > 1 and sys.argv[1] == "fma"))
+    if len(sys.argv) > 1 and sys.argv[1] == "baseline":
+        main_baseline()
+    else:
+        main(fast=(len(sys.argv) > 1 and sys.argv[1] == "fma"))
