@@ -89,6 +89,8 @@ struct girih_gpu_ctx {
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_x = nullptr, ev_y = nullptr;
   std::vector<EvPair> comm_ev;
   size_t comm_ev_used = 0;
+  std::vector<EvPair> comp_ev;        // one pair around every sweep of a run: "compute" is their sum, not total - comm
+  size_t comp_ev_used = 0;
   bool uploaded = false, frames_equal = true, static_halo_done = false;
   bool frames_dirty = false;   // fields were replaced on the device since frames_equal was evaluated (upload_fields / commit_fields)
   // NCCL
@@ -272,6 +274,7 @@ extern "C" void girih_gpu_destroy(girih_gpu_ctx *c) {
   girih_gpu_peer_detach(c);
   if (c->d_flags) cudaFree(c->d_flags);
   for (auto &p : c->comm_ev) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto &p : c->comp_ev) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
   if (c->ev_x) cudaEventDestroy(c->ev_x);
@@ -1054,6 +1057,7 @@ static int begin_run(girih_gpu_ctx *c) {
   CU(cudaSetDevice(c->device));
   c->n_kernels = c->n_passes = c->n_steps = 0;
   c->comm_ev_used = 0;
+  c->comp_ev_used = 0;
   c->ms_compute = c->ms_comm = c->ms_total = 0;
   if (c->d_flags) CU(cudaMemsetAsync(c->d_flags + 2, 0, sizeof(int), c->s_comp));   // "a halo-push wait gave up" is per run
   CU(cudaEventRecord(c->ev_t0, c->s_comp));
@@ -1086,7 +1090,13 @@ static int end_run(girih_gpu_ctx *c) {
     comm += m;
   }
   c->ms_comm = comm;
-  c->ms_compute = c->ms_total;   // kernels run back to back on the compute stream
+  double comp = 0;   // time the compute stream spent inside sweeps (waits for exchanges / neighbours are outside the pairs)
+  for (size_t i = 0; i < c->comp_ev_used; ++i) {
+    float m = 0;
+    CU(cudaEventElapsedTime(&m, c->comp_ev[i].a, c->comp_ev[i].b));
+    comp += m;
+  }
+  c->ms_compute = comp;
   return GIRIH_OK;
 }
 
@@ -1141,6 +1151,22 @@ static int halo_group(const girih_gpu_ctx *c, int T, bool overlap) {
   return k;
 }
 
+// launch_pass bracketed by a cudaEvent pair on the compute stream (the run's "compute" time is the sum of the pairs)
+static cudaError_t timed_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb0, int ze0, int zb1 = 0, int ze1 = 0) {
+  if (c->comp_ev_used == c->comp_ev.size()) {
+    EvPair p;
+    cudaError_t e = cudaEventCreate(&p.a);
+    if (e == cudaSuccess) e = cudaEventCreate(&p.b);
+    if (e != cudaSuccess) return e;
+    c->comp_ev.push_back(p);
+  }
+  EvPair &p = c->comp_ev[c->comp_ev_used++];
+  cudaError_t e = cudaEventRecord(p.a, c->s_comp);
+  if (e == cudaSuccess) e = launch_pass(c, T, src, dst, zb0, ze0, zb1, ze1);
+  if (e == cudaSuccess) e = cudaEventRecord(p.b, c->s_comp);
+  return e;
+}
+
 static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur, bool overlap) {
   const DevGrid &g = c->g;
   const int r = g.r;
@@ -1190,7 +1216,7 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
       CU(cudaGetLastError());
       c->n_kernels++;
       c->push_planes = (p + 1 < sizes.size()) ? sizes[p + 1] * r : 0;   // what the next pass reads beyond its slab
-      cudaError_t le = launch_pass(c, T, src, dst, zb, ze);
+      cudaError_t le = timed_pass(c, T, src, dst, zb, ze);
       c->push_planes = 0;
       CU(le);
       CU(signal());
@@ -1208,7 +1234,7 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
       // planes beyond the slab that later passes of this group read: computed here, towards neighbours only
       const int ext = ready - T * r;
       const int lo = (neighbour(c, 2, -1) >= 0) ? ext : 0, hi = (neighbour(c, 2, +1) >= 0) ? ext : 0;
-      CU(launch_pass(c, T, src, dst, zb - lo, ze + hi));
+      CU(timed_pass(c, T, src, dst, zb - lo, ze + hi));
       ready = ext;
       cur = dst;
       c->n_passes++;
@@ -1235,7 +1261,7 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
       // the sweep of the inner half
       const int zq = std::max(nd, g.nz / 4);
       const bool need_dn = neighbour(c, 2, -1) >= 0, need_up = neighbour(c, 2, +1) >= 0;
-      CU(launch_pass(c, T, src, dst, zb, zb + zq, ze - zq, ze));
+      CU(timed_pass(c, T, src, dst, zb, zb + zq, ze - zq, ze));
       CU(cudaEventRecord(c->ev_y, c->s_comp));
       CU(cudaStreamWaitEvent(c->s_comm, c->ev_y, 0));
       if (c->comm_ev_used == c->comm_ev.size()) {
@@ -1265,11 +1291,11 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
         if ((rc = exchange_z(c, c->dU[dst], nd, c->s_comm))) return rc;
       }
       CU(cudaEventRecord(q.b, c->s_comm));
-      CU(launch_pass(c, T, src, dst, zb + zq, ze - zq));
+      CU(timed_pass(c, T, src, dst, zb + zq, ze - zq));
       CU(cudaStreamWaitEvent(c->s_comp, q.b, 0));   // my next-but-one outer sweep overwrites what this exchange reads
       ready = nd;
     } else {
-      CU(launch_pass(c, T, src, dst, zb, ze));
+      CU(timed_pass(c, T, src, dst, zb, ze));
       ready = 0;
     }
     cur = dst;

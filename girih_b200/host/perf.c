@@ -9,9 +9,11 @@
  * GStencil/s quirk (MEDIAN multiplies by nt, MIN/MAX use the per-step time, src/utils.c:872-875).
  */
 #define _POSIX_C_SOURCE 200112L
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "girih_host.h"
 
@@ -21,9 +23,45 @@ static int cmp_double(const void *a, const void *b) {
 }
 
 static double hbm_peak_gbs(void) {
-  /* measured copy bandwidth of this pool's B200 (MEASURED_PEAKS.json); override with GIRIH_HBM_GBS */
+  /* measured copy bandwidth of this pool's B200: GIRIH_HBM_GBS, else "hbm_gbs" of MEASURED_PEAKS.json (driver-written;
+   * $GIRIH_PEAKS_FILE, ./MEASURED_PEAKS.json or the one next to the build directory of this executable), else the
+   * last value the driver measured (6545.6) */
   const char *e = getenv("GIRIH_HBM_GBS");
-  return e ? atof(e) : 6538.9;
+  char exe[4096], path[4200];
+  const char *cands[3];
+  int i, n = 0;
+  ssize_t len;
+  if (e) return atof(e);
+  cands[n++] = getenv("GIRIH_PEAKS_FILE");
+  cands[n++] = "MEASURED_PEAKS.json";
+  len = readlink("/proc/self/exe", exe, sizeof(exe) - 1);
+  path[0] = 0;
+  if (len > 0) {
+    char *slash;
+    exe[len] = 0;
+    slash = strrchr(exe, '/');
+    if (slash) { *slash = 0; slash = strrchr(exe, '/'); }
+    if (slash) { *slash = 0; snprintf(path, sizeof(path), "%s/MEASURED_PEAKS.json", exe); }
+  }
+  cands[n++] = path[0] ? path : NULL;
+  for (i = 0; i < n; i++) {
+    FILE *f;
+    if (!cands[i]) continue;
+    f = fopen(cands[i], "r");
+    if (f) {
+      char buf[4096];
+      size_t got = fread(buf, 1, sizeof(buf) - 1, f);
+      const char *k;
+      fclose(f);
+      buf[got] = 0;
+      k = strstr(buf, "\"hbm_gbs\"");
+      if (k && (k = strchr(k, ':')) != NULL) {
+        const double v = atof(k + 1);
+        if (v > 100.0) return v;
+      }
+    }
+  }
+  return 6545.6;
 }
 
 static void performance_results(Parameters *p, double t, double t_max, double t_min, double t_med,

@@ -34,9 +34,13 @@ static void finish(Parameters *p, int rc, const char *what) {
   girih_gpu_last_launch_info(p->gpu, &nk, &np, &ns, &tf);
   p->steps_executed = ns;
   p->tfuse_used = tf;
-  /* Profile fields as the reference fills them (src/kernels/nb_naive_ts.c:201-202) */
-  p->prof.compute += 1e-3 * (total - comm > 0 ? total - comm : total);
+  /* Profile fields as the reference fills them (src/kernels/nb_naive_ts.c:201-202): compute = device time inside the
+   * sweeps (cudaEvent pairs around every launch), communicate = device time of the exchanges on the comm stream (with
+   * the overlapped schedules it runs under the sweeps, so the two may add up to more than the total), wait = what is
+   * left of the total: the compute stream waiting for an exchange or for a neighbour */
+  p->prof.compute += 1e-3 * comp;
   p->prof.communicate += 1e-3 * comm;
+  p->prof.wait += 1e-3 * (total - comp > 0 ? total - comp : 0);
   p->prof.total = 1e-3 * total;
 }
 
