@@ -118,6 +118,7 @@ struct girih_gpu_ctx {
   bool peer_ipc[2] = {false, false};      // mapped with cudaIpcOpenMemHandle (to be closed)
   int opt_push = 0;
   int opt_copy = 0;                       // option "halo_copy": overlapped passes move their halos with the copy engines
+  int opt_zwave = 0, opt_zwave_block = 0; // options "zwave" (time steps in flight, 0 = choose) / "zwave_block" (planes per launch)
   int push_seq = 0;                       // passes signalled so far (the same number on every rank)
   int push_planes = 0;                    // planes the pass being launched pushes to each neighbour (0 = none)
   cudaEvent_t ev_in_ready = nullptr, ev_in_free = nullptr, ev_out_ready = nullptr, ev_out_free = nullptr;
@@ -313,6 +314,8 @@ extern "C" int girih_gpu_set_option(girih_gpu_ctx *c, const char *key, int value
   else if (!strcmp(key, "halo_group")) c->opt_halo_group = value;
   else if (!strcmp(key, "halo_push")) c->opt_push = value;
   else if (!strcmp(key, "halo_copy")) c->opt_copy = value;
+  else if (!strcmp(key, "zwave")) c->opt_zwave = value;
+  else if (!strcmp(key, "zwave_block")) c->opt_zwave_block = value;
   else return fail(c, GIRIH_ERR_ARG, "unknown option '%s'", key);
   return GIRIH_OK;
 }
@@ -1096,7 +1099,7 @@ static int end_run(girih_gpu_ctx *c) {
     CU(cudaEventElapsedTime(&m, c->comp_ev[i].a, c->comp_ev[i].b));
     comp += m;
   }
-  c->ms_compute = comp;
+  c->ms_compute = c->comp_ev_used ? comp : c->ms_total - comm;
   return GIRIH_OK;
 }
 
@@ -1377,6 +1380,49 @@ extern "C" int girih_gpu_run_single(girih_gpu_ctx *c, int nsteps, int overlap) {
   return end_run(c);
 }
 
+// z-wavefront temporal blocking THROUGH L2 for the operators that have no fused-sweep kernel (radius 4: slots 0 and 4;
+// the box operator): the GPU form of the reference's wavefront (src/kernels/stencils_1wf.ic:37-77: W time steps in
+// flight along z, each lagging the previous one by r planes, `kt -= NHALO`) with the 126 MB L2 in the role of the CPU's
+// last-level cache.  The slab is swept in blocks of B planes; step s of a group of W steps follows step s-1 at a
+// distance of r planes, so what step s reads -- the planes step s-1 has just written and the planes it read -- is still
+// in L2: W steps cost about one read and one write of each array from HBM instead of W.  Every launch is the ordinary
+// single-step kernel on a z range, so the result is bit-identical by construction.
+//   step s of a group reads array cur ^ (s & 1) and writes the other one
+//   RAW: step s stops r planes below the last plane step s-1 has completed (or runs to the end once step s-1 is done)
+//   WAR: the planes step s overwrites lie below everything step s-1 still has to read (same distance r)
+static int run_zwave(girih_gpu_ctx *c, int nsteps, int W, int B, int &cur) {
+  const DevGrid &g = c->g;
+  const int r = g.r, zb = g.Z0, ze = g.Z0 + g.nz;
+  int done = 0;
+  std::vector<int> hi;
+  while (done < nsteps) {
+    const int w = std::min(W, nsteps - done);
+    hi.assign((size_t)w, zb);
+    while (hi[w - 1] < ze) {
+      for (int s = 0; s < w; ++s) {
+        const int limit = (s == 0) ? std::min(ze, hi[0] + B) : (hi[s - 1] >= ze ? ze : hi[s - 1] - r);
+        if (limit > hi[s]) {
+          const int src = cur ^ (s & 1);
+          CU(launch_pass(c, 1, src, src ^ 1, hi[s], limit));   // (no event pair per launch: there are thousands)
+          hi[s] = limit;
+        }
+      }
+    }
+    done += w;
+    c->n_passes++;
+    c->n_steps += w;
+    if (w & 1) cur ^= 1;
+  }
+  return GIRIH_OK;
+}
+
+// steps in flight of the z wavefront for this context (1 = plain single steps)
+static int zwave_depth(const girih_gpu_ctx *c) {
+  if (c->nranks != 1 || xy_decomposed(c) || c->kd.max_tfuse > 1 || c->opt_variant == 1) return 1;
+  if (c->opt_zwave > 0) return c->opt_zwave;
+  return 1;
+}
+
 extern "C" int girih_gpu_run_fused(girih_gpu_ctx *c, int nsteps, int tfuse) {
   if (!c || nsteps < 0) return GIRIH_ERR_ARG;
   int T = tfuse;
@@ -1393,7 +1439,12 @@ extern "C" int girih_gpu_run_fused(girih_gpu_ctx *c, int nsteps, int tfuse) {
   std::vector<int> sizes;
   plan_passes(nsteps, T, sizes);
   int cur = 1;
-  if ((rc = run_passes(c, sizes, cur, c->opt_overlap != 0))) return rc;
+  const int W = zwave_depth(c);
+  if (T == 1 && W > 1) {
+    const int B = c->opt_zwave_block > 0 ? c->opt_zwave_block : 8;
+    if ((rc = run_zwave(c, nsteps, W, B, cur))) return rc;
+    T = W;
+  } else if ((rc = run_passes(c, sizes, cur, c->opt_overlap != 0))) return rc;
   if (nsteps > 0 && cur != ((nsteps % 2 == 1) ? 0 : 1))
     return fail(c, GIRIH_ERR_STATE, "internal: pass schedule left the newest level in the wrong array");
   if ((rc = finish_halos(c))) return rc;

@@ -205,8 +205,12 @@ static cudaError_t launch_r1_tile(const StreamLaunch &s) {
     if (s.tile == 310) return launch_r1_t<K, R, T, 3, 10>(s);
     if (s.tile == 316) return launch_r1_t<K, R, T, 3, 16>(s);
   }
-  // defaults from the B200 sweep: fp64 constant coefficients run best with 4 rows per thread and 8
-  // warps (fewest shared-memory exchanges per point), everything else with 2 rows and 16 warps
+  // defaults from the B200 sweeps (profiles/kernel_sweep_r01.md, profiles/r02_kbench_k1_tiles.log).  Slot 1 in fp64,
+  // strict arithmetic: 2 rows x 16 warps with the split barrier is the fastest tile at every fused depth
+  // (T = 4: 0.892 vs 0.917 ms per pass at 512^3, T = 3: 0.700 vs 0.848, T = 2: 0.562 vs 0.648)
+  if constexpr (K == 1 && sizeof(R) == 8 && T >= 2) return launch_r1_t<K, R, T, 2, 16, R1_SPLIT>(s);
+  // otherwise fp64 constant coefficients run best with 4 rows per thread and 8 warps (fewest shared-memory
+  // exchanges per point), everything else with 2 rows and 16 warps
   if constexpr (KTraits<K>::NCA == 0 && sizeof(R) == 8) return launch_r1_t<K, R, T, 4, 8>(s);
   else return launch_r1_t<K, R, T, 2, 16>(s);
 }
