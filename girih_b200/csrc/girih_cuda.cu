@@ -1046,11 +1046,13 @@ static cudaError_t launch_pass(girih_gpu_ctx *c, int T, int src, int dst, int zb
 // every fused level, so the gain shrinks (slot 2, 3) or vanishes (slot 5: 9 words per update).
 static int default_tfuse(const girih_gpu_ctx *c) {
   switch (c->kernel) {
-    // fastest measured depth per (operator, precision) at 512^3, profiles/kernel_sweep_r01.md
+    // fastest measured depth per (operator, precision) at 512^3: profiles/kernel_sweep_r01.md and the round-2 sweep
+    // profiles/r02_kbench_others.log (with the trapezoid-skip tile the fp64 per-point-coefficient operators gain from
+    // depth 2: slot 3 168.8 vs 145.6 GLUP/s, slot 5 105.8 vs 98.8, slot 2 256.4 vs 192.5; slot 3 fp32 353.8 at depth 3)
     case 1: return 4;
     case 2: return c->es == 8 ? 2 : 3;
-    case 3: return c->es == 8 ? 1 : 2;
-    case 5: return c->es == 8 ? 1 : 2;
+    case 3: return c->es == 8 ? 2 : 3;
+    case 5: return 2;
     default: return 1;
   }
 }
