@@ -93,6 +93,8 @@ struct girih_gpu_ctx {
   size_t comp_ev_used = 0;
   bool uploaded = false, frames_equal = true, static_halo_done = false;
   bool frames_dirty = false;   // fields were replaced on the device since frames_equal was evaluated (upload_fields / commit_fields)
+  unsigned long long *h_fflag = nullptr;   // page-locked, device-mapped word the frame check writes (no copy engine involved:
+                                           // a D2H copy would queue behind the asynchronous download of the previous job)
   // NCCL
   ncclComm_t comm = nullptr;
   // options
@@ -258,6 +260,7 @@ extern "C" void girih_gpu_destroy(girih_gpu_ctx *c) {
   if (c->dU3) cudaFree(c->dU3);
   if (c->dCoef) cudaFree(c->dCoef);
   if (c->d_scan) cudaFree(c->d_scan);
+  if (c->h_fflag) cudaFreeHost(c->h_fflag);
   if (c->d_xbuf) cudaFree(c->d_xbuf);
   if (c->d_xerr) cudaFree(c->d_xerr);
   if (c->d_stage) cudaFree(c->d_stage);
@@ -487,8 +490,9 @@ __global__ void k_frame_diff(DevGrid g, const R *__restrict__ a, const R *__rest
 
 static int refresh_frames_equal(girih_gpu_ctx *c) {
   if (!c->frames_dirty) return GIRIH_OK;
-  unsigned long long *flag = c->d_scan + 2;
-  CU(cudaMemsetAsync(flag, 0, sizeof(*flag), c->s_comp));
+  if (!c->h_fflag) CU(cudaHostAlloc((void **)&c->h_fflag, sizeof(unsigned long long), cudaHostAllocMapped));
+  unsigned long long *flag = c->h_fflag;   // unified addressing: the host pointer is valid on the device
+  *flag = 0ull;
   const int zf = c->coords[2] == 0, zl = c->coords[2] == c->dims[2] - 1;
   if (c->es == 8) {
     auto k = k_frame_diff<double>;
@@ -498,10 +502,8 @@ static int refresh_frames_equal(girih_gpu_ctx *c) {
     GIRIH_LAUNCH(k, 148 * 8, 128, 0, c->s_comp, c->g, (const float *)c->dU[0], (const float *)c->dU[1], c->hshape[1], c->hshape[2], zf, zl, flag);
   }
   CU(cudaGetLastError());
-  unsigned long long h = 0;
-  CU(cudaMemcpyAsync(&h, flag, sizeof(h), cudaMemcpyDeviceToHost, c->s_comp));
   CU(cudaStreamSynchronize(c->s_comp));
-  c->frames_equal = (h == 0);
+  c->frames_equal = (*(volatile unsigned long long *)flag == 0);
   c->frames_dirty = false;
   return GIRIH_OK;
 }

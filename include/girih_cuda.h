@@ -112,7 +112,12 @@ int girih_gpu_comm_init(girih_gpu_ctx *ctx, const void *id, size_t len);
  * girih_gpu_set_option("halo_push", 1) the fused passes of slot 1 then store their boundary planes straight into the
  * neighbours' halo planes while they sweep; a pass starts when both neighbours have flagged the end of the previous
  * one (device-side flags, no host synchronisation, no NCCL kernel between passes).  NCCL still carries the first and
- * the last exchange of a run.  Every rank must make the same calls. */
+ * the last exchange of a run.  Every rank must make the same calls.
+ * Halo copy (round 2, the schedule bench.py --gpus N measures): girih_gpu_set_option("halo_copy", 1) with the same
+ * mappings keeps the order of halo_first_ts.c:156-194 -- the outer parts of the slab first, exchange, inner part --
+ * and lets the COPY ENGINES move the halos: cudaMemcpyAsync from this rank's top / bottom planes into the
+ * neighbours' halo planes on the comm stream plus a flag word, under the sweep of the inner part (an NCCL kernel
+ * in that place takes SMs from a sweep that fills whole waves).  Every operator and both steppers; z-slabs only. */
 #define GIRIH_PEER_BLOB_BYTES 256
 int girih_gpu_peer_export(girih_gpu_ctx *ctx, void *blob, size_t len);
 int girih_gpu_peer_attach(girih_gpu_ctx *ctx, int which, const void *blob, size_t len);
@@ -231,6 +236,14 @@ int girih_gpu_scan_u1(girih_gpu_ctx *ctx, uint64_t *n_nan_inf, uint64_t *n_zero)
  *              the interior (default 0: one exchange per pass, ordered before it, measured faster)
  *   "halo_group" z-slab runs of first-order-in-time operators: fused passes served by one halo exchange
  *              (0 = choose: up to 4 while the recomputed planes stay below 1/16 of the thinnest slab)
+ *   "halo_copy" / "halo_push"  see girih_gpu_peer_export above
+ *   "zwave", "zwave_block"  operators without a fused-sweep kernel (radius 4, box), one slab: run_fused keeps
+ *              `zwave` time steps in flight along z, each r planes behind the previous one, in blocks of
+ *              `zwave_block` planes (the reference's wavefront, src/kernels/stencils_1wf.ic:37-77, with the L2 as
+ *              the cache).  Default 0 = plain single steps: measured no faster on B200.
+ *   "tile" 10408 / 10216 (slot 1, fp64, depth >= 3): exact, non-overlapping tiles whose rims travel between
+ *              co-resident CTAs through L2 (kernels_r1x.cuh; falls back to the overlapped tiles when the plane
+ *              needs more tiles than the device has SMs)
  *   "contract" arithmetic of the per-point expression.  0 (default): every product and sum rounded
  *              separately -- bit-identical to the reference built without FMA (conf/make.conf.gcc, `-O3`)
  *              and to its -O0 verifier (src/verification.c).  1: the fused multiply-adds gcc emits for the

@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -212,6 +213,9 @@ cudaError_t cudaSetDevice(int d);
 cudaError_t cudaMalloc(void **p, size_t bytes);  // 256-byte aligned like the real allocator, poisoned
 template <typename T> static inline cudaError_t cudaMalloc(T **p, size_t bytes) { return cudaMalloc((void **)p, bytes); }
 cudaError_t cudaFree(void *p);
+enum { cudaHostAllocMapped = 2 };
+static inline cudaError_t cudaHostAlloc(void **p, size_t bytes, unsigned) { *p = calloc(1, bytes); return *p ? cudaSuccess : cudaErrorInvalidValue; }
+static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 cudaError_t cudaMemset(void *p, int v, size_t bytes);
 cudaError_t cudaMemcpy(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind);
 cudaError_t cudaMemcpy3D(const cudaMemcpy3DParms *p);
