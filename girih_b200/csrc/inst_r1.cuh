@@ -77,7 +77,7 @@ static cudaError_t launch_r1_t(const StreamLaunch &s) {
 
 // Exact (non-overlapping) tiles with edge hand-off between co-resident CTAs (kernels_r1x.cuh).  Needs one resident CTA
 // per tile and z chunk: cudaErrorNotSupported tells the caller to take the overlapped-tile kernel instead.
-template <int K, typename R, int T, int PY, int NW, bool FM = false>
+template <int K, typename R, int T, int PY, int NW, bool FM = false, int XDBG = 0>
 static cudaError_t launch_r1x_t(const StreamLaunch &s) {
   if constexpr (sizeof(R) != 8 || T < 3) {
     return cudaErrorNotSupported;
@@ -108,7 +108,7 @@ static cudaError_t launch_r1x_t(const StreamLaunch &s) {
     a.xbuf = s.xbuf;
     a.err = s.xerr;
     a.seq0 = *s.xseq;
-    auto kfn = k_r1x<K, R, T, PY, NW, FM>;
+    auto kfn = k_r1x<K, R, T, PY, NW, FM, XDBG>;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) return e;
     dim3 grid(ntx, nty, nch);
@@ -151,6 +151,18 @@ static cudaError_t launch_r1_tile(const StreamLaunch &s) {
       cudaError_t e = cudaErrorNotSupported;
       if (s.tile == 10408) e = s.contract ? launch_r1x_t<K, R, T, 4, 8, true>(s) : launch_r1x_t<K, R, T, 4, 8, false>(s);
       if (s.tile == 10216) e = s.contract ? launch_r1x_t<K, R, T, 2, 16, true>(s) : launch_r1x_t<K, R, T, 2, 16, false>(s);
+#ifdef GIRIH_PERF_EXPERIMENTS
+      if constexpr (T == 4) {   // parts of the exchange removed (results INVALID): what each part costs per iteration
+        if (s.tile == 11408) e = launch_r1x_t<K, R, T, 4, 8, false, 1>(s);
+        if (s.tile == 12408) e = launch_r1x_t<K, R, T, 4, 8, false, 2>(s);
+        if (s.tile == 13408) e = launch_r1x_t<K, R, T, 4, 8, false, 3>(s);
+        if (s.tile == 17408) e = launch_r1x_t<K, R, T, 4, 8, false, 7>(s);
+        if (s.tile == 13216) e = launch_r1x_t<K, R, T, 2, 16, false, 3>(s);
+        if (s.tile == 17216) e = launch_r1x_t<K, R, T, 2, 16, false, 7>(s);
+        if (s.tile == 18408) e = launch_r1x_t<K, R, T, 4, 8, false, 11>(s);   // rim values parked in shared memory only
+        if (s.tile == 18216) e = launch_r1x_t<K, R, T, 2, 16, false, 11>(s);
+      }
+#endif
       if (e != cudaErrorNotSupported) return e;
     }
   }

@@ -104,6 +104,9 @@ cudaError_t launch_r4(int kernel, int es, const StreamLaunch &s) {
     if (s.tile == 8) return es == 8 ? launch_r4_t<0, double, 8>(s) : launch_r4_t<0, float, 8>(s);
     if (s.tile == 16) return es == 8 ? launch_r4_t<0, double, 16>(s) : launch_r4_t<0, float, 16>(s);
     if (s.tile == 116) return es == 8 ? launch_r4_async_t<0, double, 16>(s) : launch_r4_async_t<0, float, 16>(s);
+    // 2 rows per thread (the strip kernel of slot 4): fewer shared-memory bytes and instructions per update
+    if (s.tile == 208) return es == 8 ? launch_r4_strip_t<0, double, 2, 8>(s) : launch_r4_strip_t<0, float, 2, 8>(s);
+    if (s.tile == 216) return es == 8 ? launch_r4_strip_t<0, double, 2, 16>(s) : launch_r4_strip_t<0, float, 2, 16>(s);
     return es == 8 ? launch_r4_async_t<0, double, 8>(s) : launch_r4_async_t<0, float, 8>(s);
   }
   if (kernel == 4) {

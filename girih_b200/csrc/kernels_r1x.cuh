@@ -63,7 +63,8 @@ template <typename R, int T, int PY, int NW> struct R1xCfg {
   static constexpr size_t TILE_BYTES = (size_t)RING * RING_SLOTS * 16;
   static constexpr size_t EDGE_BYTES = (size_t)T * 2 * (NW + 2) * 2 * WX * sizeof(R);
   static constexpr size_t XS_BYTES = (size_t)NW * T * 2 * PY * sizeof(R);
-  static constexpr size_t SMEM = EDGE_BYTES + XS_BYTES;
+  static constexpr size_t XO_BYTES = (size_t)NW * NXS * sizeof(R);
+  static constexpr size_t SMEM = EDGE_BYTES + XS_BYTES + XO_BYTES;
   static_assert(T >= 2 && NW >= 2 && NXS <= 32, "one x slot per lane and stage; first and last warp are distinct");
 };
 
@@ -71,26 +72,45 @@ template <typename R, int T, int PY, int NW> struct R1xCfg {
 constexpr unsigned R1X_SPIN_LIMIT = 1u << 22;   // polls (~0.3 us each) before a lane gives up on a slot
 #ifndef GIRIH_CUDA_EMU
 struct LLWord { unsigned lo, t0, hi, t1; };
-__device__ __forceinline__ void ll_store(void *p, double v, unsigned tag) {
+// All of these are PREDICATED single instructions, not branches: the T fused levels of an iteration must stay one
+// basic block (the scheduler overlaps one level's shuffles and loads with another level's arithmetic), and every
+// `if` around a store or a load would cut it.
+template <int OFF> __device__ __forceinline__ void ll_store_if(void *p, double v, unsigned tag) {   // no-op when p == nullptr
   const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
-  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(tag), "r"(hi), "r"(tag));
+  asm volatile("{\n.reg .pred q;\nsetp.ne.u64 q, %0, 0;\n@q st.relaxed.gpu.global.v4.u32 [%0+%5], {%1, %2, %3, %4};\n}"
+               ::"l"(p), "r"(lo), "r"(tag), "r"(hi), "r"(tag), "n"(OFF));
 }
 __device__ __forceinline__ LLWord ll_load(const void *p) {
   LLWord w;
   asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.lo), "=r"(w.t0), "=r"(w.hi), "=r"(w.t1) : "l"(p));
   return w;
 }
-__device__ __forceinline__ double ll_value(const LLWord &w) { return __hiloint2double((int)w.hi, (int)w.lo); }
-__device__ __forceinline__ LLWord ll_pack(double v, unsigned tag) {
-  LLWord w;
-  w.lo = (unsigned)__double2loint(v); w.hi = (unsigned)__double2hiint(v); w.t0 = w.t1 = tag;
-  return w;
+__device__ __forceinline__ void ll_load_if(bool pred, const void *p, LLWord &w) {   // w keeps its value when !pred
+  asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %5, 0;\n@q ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];\n}"
+               : "+r"(w.lo), "+r"(w.t0), "+r"(w.hi), "+r"(w.t1) : "l"(p), "r"((unsigned)pred));
 }
-__device__ __forceinline__ void spin_pause() { __nanosleep(100); }
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void frame_load_if(bool pred, const double *p, double &v) {   // read-only path; v kept when !pred
+  asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.nc.f64 %0, [%1];\n@q prefetch.global.L2 [%1+%3];\n}"
+               : "+d"(v) : "l"(p), "r"((unsigned)pred), "n"(0));
+}
+__device__ __forceinline__ void prefetch_l2_if(bool pred, const void *p) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %1, 0;\n@q prefetch.global.L2 [%0];\n}" ::"l"(p), "r"((unsigned)pred));
+}
+__device__ __forceinline__ void lds_if(bool pred, const double *p, double &v) {   // shared memory; v kept when !pred
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.shared.f64 %0, [%1];\n}" : "+d"(v) : "r"(a), "r"((unsigned)pred));
+}
+__device__ __forceinline__ void sts_if(bool pred, double *p, double v) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.shared.f64 [%0], %1;\n}" ::"r"(a), "d"(v), "r"((unsigned)pred) : "memory");
+}
+__device__ __forceinline__ double ll_value(const LLWord &w) { return __hiloint2double((int)w.hi, (int)w.lo); }
+__device__ __forceinline__ void spin_pause() { __nanosleep(40); }
 #endif   // the test suite's CPU SIMT emulator supplies its own versions (tests/cuda_emu)
 
-template <int K, typename R, int T, int PY, int NW, bool FM = false>
+// XDBG (timing experiments only, results INVALID; built with -DGIRIH_PERF_EXPERIMENTS): 1 = no LL publish,
+// 2 = no polls, 4 = rim columns not taken in (plain shuffles)
+template <int K, typename R, int T, int PY, int NW, bool FM = false, int XDBG = 0>
 __global__ void __launch_bounds__(32 * NW, 1)
 k_r1x(const R1xArgs<R> a) {
   using Cfg = R1xCfg<R, T, PY, NW>;
@@ -152,15 +172,12 @@ k_r1x(const R1xArgs<R> a) {
   const int nit = (ze - zb) + 2 * T;
 
   // ---- publishing: where my rim values go -------------------------------------------------------------
-  // lane 0 hands its first column to the left tile (its x+ slots), lane 31 its last column to the right tile (x- slots)
-  unsigned char *xpub = nullptr;
-  if (lane == 0 && has_xm) xpub = inb - (long long)Cfg::TILE_BYTES + (size_t)(H + warp * PY) * 16;
-  if (lane == 31 && has_xp) xpub = inb + (long long)Cfg::TILE_BYTES + (size_t)(warp * PY) * 16;
   // warp 0 hands its first row to the tile above (its y+ slots), warp NW-1 its last row to the tile below (y- slots)
   unsigned char *ypub = nullptr;
   if (warp == 0 && has_ym) ypub = inb - (long long)ni * (long long)Cfg::TILE_BYTES + (size_t)(2 * H + WX + lane * VX) * 16;
   if (warp == NW - 1 && has_yp) ypub = inb + (long long)ni * (long long)Cfg::TILE_BYTES + (size_t)(2 * H + lane * VX) * 16;
   const bool edge_warp = (warp == 0) || (warp == NW - 1);
+  const bool lane_first = lane == 0, lane_last = lane == 31;
 
   // ---- polling: the slots each lane collects ----------------------------------------------------------------
   // A rim value of level l is published in iteration g (when the stage that produces level l ends; level 0: at the top)
@@ -172,31 +189,39 @@ k_r1x(const R1xArgs<R> a) {
   //   x: lanes < NXS of every warp collect the warp's 2 * PY column values (one slot each) into xs[]
   //   y: the first / last warp collects the row above / below the tile, 2 slots per lane, into the edge rows
   // kinds: 0 none, 1 slot written by a neighbour tile, 2 Dirichlet frame cell read from the input array
+  // Level 0 is the input array itself: its rim needs no hand-over, every tile reads it from global memory like a frame
+  // cell (f0X / f0Y: is the cell allocated; fX / fY: its in-plane offset).  Only levels 1..T-1 travel through slots.
   int kX = 0, kY = 0;
   unsigned sX = 0, sY = 0;   // slot byte offset inside one (ring, level 0) block -- or in-plane element offset (kind 2)
+  unsigned fX = 0, fY = 0;
+  bool f0X = false, f0Y = false;
   int dX = 0, dY = 0;        // destination: xs index (level 0) / edge-row element offset (level 0, parity 0)
+  unsigned char *xpub8 = nullptr;   // lanes < NXS: where rim value `lane` of this warp goes (null: no tile on that side)
   if (lane < NXS) {
     const int side = lane / PY, j = lane % PY;
     const bool has = side == 0 ? has_xm : has_xp;
     dX = side * PY + j;
+    const int xc = side == 0 ? xt0 - 1 : xt0 + WX, yr = y0 + j;
+    f0X = xc >= 0 && xc < g.px && yr >= 0 && yr < g.ny_dev;
+    fX = (unsigned)(yr * g.px + xc);
     if (has) { kX = 1; sX = (unsigned)((side * H + warp * PY + j) * 16); }
-    else {
-      const int xc = side == 0 ? xt0 - 1 : xt0 + WX, yr = y0 + j;
-      kX = (xc >= 0 && xc < g.px && yr >= 0 && yr < g.ny_dev) ? 2 : 0;
-      sX = (unsigned)(yr * g.px + xc);
-    }
+    else { kX = f0X ? 2 : 0; sX = fX; }
+    // my first column goes to the left tile's x+ slots, my last column to the right tile's x- slots
+    if (has) xpub8 = (side == 0 ? inb - (long long)Cfg::TILE_BYTES + (size_t)H * 16 : inb + (long long)Cfg::TILE_BYTES) + (size_t)(warp * PY + j) * 16;
   }
   if (edge_warp) {
     const int side = warp == 0 ? 0 : 1;
     const bool has = side == 0 ? has_ym : has_yp;
     dY = (int)(edge_ptr(0, 0, NW + side, side == 0 ? 1 : 0) - edge) + lane * VX;
+    const int yr = side == 0 ? yt0 - 1 : yt0 + H;
+    f0Y = yr >= 0 && yr < g.ny_dev && x_alloc;
+    fY = (unsigned)(yr * g.px + x);
     if (has) { kY = 1; sY = (unsigned)((2 * H + side * WX + lane * VX) * 16); }
-    else {
-      const int yr = side == 0 ? yt0 - 1 : yt0 + H;
-      kY = (yr >= 0 && yr < g.ny_dev && x_alloc) ? 2 : 0;
-      sY = (unsigned)(yr * g.px + x);
-    }
+    else { kY = f0Y ? 2 : 0; sY = fY; }
   }
+  // rim values of the level a stage has just produced wait here (xo[side][row], written by lanes 0 / 31) until the warp's
+  // first NXS lanes send them off with ONE store at the start of the next stage
+  R *const xo = reinterpret_cast<R *>(smem_raw + Cfg::EDGE_BYTES + Cfg::XS_BYTES) + (size_t)warp * NXS;
   constexpr int EDGE_PAR = (NW + 2) * 2 * WX;        // elements between the two parities of one level's edge rows
   constexpr int EDGE_LVL = 2 * EDGE_PAR;             // ... between levels
 
@@ -220,23 +245,26 @@ k_r1x(const R1xArgs<R> a) {
   };
   load_plane(zb - T, S[0][2]);   // "F" of phase 0
 
-  // one slot: issue() starts the load, finish() spins until the tag of the wanted iteration is there.  A frame cell
-  // (kind 2) is read from plane zp of the input array and wrapped so that finish() accepts it at once.
+  // one slot: issue() starts the load (predicated instructions, no branch), finish() checks the tag and only then, in
+  // the rare case that the value has not arrived, leaves the straight line to wait for it.  A frame cell (kind 2) is
+  // read from plane zp of the input array and wrapped so that finish() accepts it at once.
   auto issue = [&](int kind, const unsigned char *slot, unsigned off, int zp, unsigned tag) GIRIH_LAMBDA_INLINE -> LLWord {
     LLWord w;
     w.lo = w.hi = 0u; w.t0 = w.t1 = tag;
-    if (kind == 1) w = ll_load(slot);
-    else if (kind == 2 && zp >= 0 && zp < g.nz_dev) {
-      const R *q = a.in + (long long)zp * g.pxy + off;
-      w = ll_pack(__ldg(q), tag);
-      if (zp + 2 < g.nz_dev) prefetch_l2(q + 2 * g.pxy);   // the same cell two planes on: wanted two iterations from now
-    }
+    ll_load_if(kind == 1, slot, w);
+    const bool fr = (kind == 2) && (zp >= 0) && (zp < g.nz_dev);
+    const R *q = a.in + (long long)zp * g.pxy + off;
+    R fv = (R)0;
+    frame_load_if(fr, q, fv);
+    prefetch_l2_if(fr && (zp + 2 < g.nz_dev), q + 2 * g.pxy);   // the same cell two planes on: wanted two iterations from now
+    if (kind == 2) { w.lo = (unsigned)__double2loint(fv); w.hi = (unsigned)__double2hiint(fv); }
     return w;
   };
   bool gave_up = false;   // after one time-out this lane no longer waits: the launch ends quickly and the host sees *err
   auto finish = [&](int kind, const unsigned char *slot, LLWord w, unsigned tag) GIRIH_LAMBDA_INLINE -> R {
-    if (kind == 1) {
+    if (kind == 1 && (w.t0 != tag || w.t1 != tag)) {   // rare: the neighbour is behind
       unsigned spins = 0;
+#pragma unroll 1
       while ((w.t0 != tag || w.t1 != tag) && !gave_up) {
         if (++spins > R1X_SPIN_LIMIT) { gave_up = true; *a.err = 1; break; }
         spin_pause();   // a short sleep: a warp that re-polls at once floods the slot's L2 line and delays the store it waits for
@@ -260,23 +288,40 @@ k_r1x(const R1xArgs<R> a) {
       constexpr int l = decltype(level_tag)::value;
       st128<R>(edge_ptr(l, cur, warp, 0) + lane * VX, P[0]);
       st128<R>(edge_ptr(l, cur, warp, 1) + lane * VX, P[PY - 1]);
-      constexpr size_t off = (size_t)(RING_CUR * RING_SLOTS + l * LEVEL_SLOTS) * 16;
-      if (xpub != nullptr) {
+      if constexpr (((XDBG & 1) != 0 && (XDBG & 8) == 0) || l == 0) return;   // level 0 is read from the input array by everybody
 #pragma unroll
-        for (int j = 0; j < PY; ++j) ll_store(xpub + off + (size_t)j * 16, lane == 0 ? P[j][0] : P[j][VX - 1], tag);
+      for (int j = 0; j < PY; ++j) {
+        sts_if(lane_first, xo + j, P[j][0]);
+        sts_if(lane_last, xo + PY + j, P[j][VX - 1]);
       }
-      if (ypub != nullptr) {   // warp-uniform
+    };
+    // start of stage l >= 1: the rim of level l (parked in xo by the previous stage, __syncwarp in between) leaves
+    auto send_x = [&](auto level_tag) GIRIH_LAMBDA_INLINE {
+      constexpr int l = decltype(level_tag)::value;
+      constexpr int off = (RING_CUR * RING_SLOTS + l * LEVEL_SLOTS) * 16;
+      if constexpr ((XDBG & 1) != 0 || l == 0) return;
+      R v = (R)0;
+      lds_if(xpub8 != nullptr, xo + lane, v);
+      ll_store_if<off>(xpub8, v, tag);
+    };
+    // the rows above / below the tile leave with the first / last warp: a warp-uniform branch, kept out of the hot block
+    auto publish_y = [&](auto level_tag, const R (&P)[PY][VX]) GIRIH_LAMBDA_INLINE {
+      constexpr int l = decltype(level_tag)::value;
+      constexpr int off = (RING_CUR * RING_SLOTS + l * LEVEL_SLOTS) * 16;
+      if constexpr ((XDBG & 1) != 0 || l == 0) return;
+      if (ypub != nullptr) {
         if (warp == 0) {
-#pragma unroll
-          for (int e = 0; e < VX; ++e) ll_store(ypub + off + (size_t)e * 16, P[0][e], tag);
+          ll_store_if<off>(ypub, P[0][0], tag);
+          ll_store_if<off + 16>(ypub, P[0][VX - 1], tag);
         } else {
-#pragma unroll
-          for (int e = 0; e < VX; ++e) ll_store(ypub + off + (size_t)e * 16, P[PY - 1][e], tag);
+          ll_store_if<off>(ypub, P[PY - 1][0], tag);
+          ll_store_if<off + 16>(ypub, P[PY - 1][VX - 1], tag);
         }
       }
     };
 
     publish(Level<0>{}, S[0][iF]);
+    publish_y(Level<0>{}, S[0][iF]);
 
     R Ofin[PY][VX];
     auto level = [&](auto level_tag) GIRIH_LAMBDA_INLINE {
@@ -295,15 +340,14 @@ k_r1x(const R1xArgs<R> a) {
       const bool pactive = !PREV || it > 0;
       const unsigned char *const px0 = inb + (size_t)(RING_P * RING_SLOTS + lv * LEVEL_SLOTS) * 16 + sX;
       const unsigned char *const py0 = inb + (size_t)(RING_P * RING_SLOTS + lv * LEVEL_SLOTS) * 16 + sY;
-      const int kx = pactive ? kX : 0, ky = (pactive && edge_warp) ? kY : 0;
-      LLWord wx = issue(kx, px0, sX, zp, ptag);
-      LLWord wy0, wy1;
-      wy0.lo = wy0.hi = 0u; wy0.t0 = wy0.t1 = ptag;
-      wy1 = wy0;
-      if (edge_warp) {   // warp-uniform
-        wy0 = issue(ky, py0, sY, zp, ptag);
-        wy1 = issue(ky, py0 + 16, sY + 1u, zp, ptag);
-      }
+      // level 0 (PREV == false): the cell of the input array, whatever the tile's position
+      const int kx = (XDBG & 2) ? 0 : (PREV ? (pactive ? kX : 0) : (f0X ? 2 : 0));
+      const int ky = ((XDBG & 2) || !edge_warp) ? 0 : (PREV ? (pactive ? kY : 0) : (f0Y ? 2 : 0));
+      const unsigned ox = PREV ? sX : fX, oy = PREV ? sY : fY;
+      send_x(Level<l>{});
+      LLWord wx = issue(kx, px0, ox, zp, ptag);
+      LLWord wy0 = issue(ky, py0, oy, zp, ptag);            // predicated off everywhere but in the first / last warp
+      LLWord wy1 = issue(ky, py0 + 16, oy + 1u, zp, ptag);
 
       // rows just outside my strip: neighbouring warps, or (first / last warp) the neighbouring tiles
       R up[VX], dn[VX];
@@ -331,9 +375,10 @@ k_r1x(const R1xArgs<R> a) {
           }
           R left = __shfl_up_sync(0xffffffffu, Cp[j][VX - 1], 1);
           R right = __shfl_down_sync(0xffffffffu, Cp[j][0], 1);
-          const R xvj = xq[j];
-          left = (lane == 0) ? xvj : left;
-          right = (lane == 31) ? xvj : right;
+          if constexpr ((XDBG & 4) == 0) {   // lane 0 / 31: the neighbour tile's column instead of the shuffle's own value
+            lds_if(lane_first, xq + j, left);
+            lds_if(lane_last, xq + j, right);
+          }
 #pragma unroll
           for (int e = 0; e < VX; ++e) {
             RegNb1<R> n;
@@ -366,6 +411,7 @@ k_r1x(const R1xArgs<R> a) {
       if constexpr (l + 1 < T) stage(S[l + 1][iF]);
       else stage(Ofin);
       if constexpr (l == 0) load_plane(zin + 1, S[0][iB], it + 1 < nit);
+      if constexpr (l + 1 < T) publish_y(Level<l + 1>{}, S[l + 1][iF]);
 
       // ---- finish this stage's poll round: payloads into shared memory, for the next stage of this warp --------
 #ifdef GIRIH_R1X_TRACE

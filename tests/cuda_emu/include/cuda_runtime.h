@@ -281,7 +281,14 @@ static inline LLWord ll_pack(double v, unsigned tag) {
   return LLWord{(unsigned)b, tag, (unsigned)(b >> 32), tag};
 }
 static inline void spin_pause() { cuda_emu::coop_pause(); }
-static inline void prefetch_l2(const void *) {}
+template <int OFF> static inline void ll_store_if(void *p, double v, unsigned tag) { if (p) ll_store((unsigned char *)p + OFF, v, tag); }
+static inline void ll_load_if(bool pred, const void *p, LLWord &w) { if (pred) w = ll_load(p); }
+static inline void frame_load_if(bool pred, const double *p, double &v) { if (pred) v = *p; }
+static inline void prefetch_l2_if(bool, const void *) {}
+static inline void lds_if(bool pred, const double *p, double &v) { if (pred) v = *p; }
+static inline void sts_if(bool pred, double *p, double v) { if (pred) *p = v; }
+static inline int __double2loint(double v) { unsigned long long b; memcpy(&b, &v, 8); return (int)(unsigned)b; }
+static inline int __double2hiint(double v) { unsigned long long b; memcpy(&b, &v, 8); return (int)(unsigned)(b >> 32); }
 // mbarrier word: [phase:32][expected:16][pending:16]; all fibers of a CTA run on one OS thread
 static inline void sb_init(unsigned long long *bar, int count) { *bar = ((unsigned long long)count << 16) | (unsigned)count; }
 static inline void sb_arrive(unsigned long long *bar) {
