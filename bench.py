@@ -534,7 +534,7 @@ def main_ours(args):
                 traffic = json.load(open(tp)).get(f"k_r1_T{T_used}_fp64_512", None)
             except Exception:   # noqa: BLE001
                 traffic = None
-        roof = {"bound": "hbm", "kernel": f"k_r1<slot 1, double, T={T_used}> (fused z-streamed sweep)",
+        roof = {"bound": "hbm", "kernel": f"k_r1<slot 1, double, T={T_used}, 2 rows x 16 warps, split barrier> (fused z-streamed sweep)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_pass,
                 "fused_steps_per_launch": T_used,
@@ -546,8 +546,8 @@ def main_ours(args):
                               "useful_instr_per_s": fp_ops * NX * NY * NZ * T_used / (ms_pass * 1e-3),
                               "peak_instr_per_s": 148 * 64 * 1.965e9,
                               "frac_useful": fp_ops * NX * NY * NZ * T_used / (ms_pass * 1e-3) / (148 * 64 * 1.965e9),
-                              "note": "ncu: FP64 pipe 55% (strict) / 42% (contract) busy incl. the recomputed tile "
-                                      "overlap (profiles/ncu_r01_fused_T4.md, ncu_r01_fused_T4_contract.md)"},
+                              "note": "ncu: FP64 pipe 61% busy, issue slots 64%, incl. the recomputed tile overlap "
+                                      "(profiles/ncu_r02_fused_T4.md; contract: ncu_r01_fused_T4_contract.md)"},
                 "single_step_pass": {"kernel": "k_r1_march<slot 1, double> (ts 0/1 and the last step of ts 2)",
                                      "ms_per_launch": ms_single,
                                      "achieved": alg_bytes / (ms_single * 1e-3) / 1e9,

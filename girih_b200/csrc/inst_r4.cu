@@ -93,10 +93,13 @@ static cudaError_t launch_r4_async_t(const StreamLaunch &s) {
 
 cudaError_t launch_r4(int kernel, int es, const StreamLaunch &s) {
   // tile option = warps (rows) per CTA
-  // tile option: 8 / 16 = ring variant with that many rows per CTA, 116 = cp.async variant with 16 rows;
-  // default = cp.async variant, 8 rows per CTA (measured fastest: 88-90% of the HBM peak at 512^3)
+  // tile option: 8 / 16 = ring variant with that many rows per CTA, 108 / 116 = cp.async variant with 8 / 16 rows;
+  // default = cp.async variant with 16 rows per CTA.  Round 1 chose 8 rows on single-pass times at 512^3; sustained over
+  // 200 steps (what the BASELINE configs run, under the 1 000 W cap) 16 rows are faster at every size: fp64 168 / 179 /
+  // 161 against 154 / 154 / 151 GLUP/s at 512^3 / 768^3 / 1024^3, fp32 364 / 356 / 358 against 346 / 341 / 336
+  // (profiles/r02_k0_sustained.log).  The 2-rows-per-thread strip kernel of slot 4 was tried for slot 0: 114 / 234 GLUP/s.
   if (s.contract) {   // contracted arithmetic: default kernels only
-    if (kernel == 0) return es == 8 ? launch_r4_async_t<0, double, 8, true>(s) : launch_r4_async_t<0, float, 8, true>(s);
+    if (kernel == 0) return es == 8 ? launch_r4_async_t<0, double, 16, true>(s) : launch_r4_async_t<0, float, 16, true>(s);
     if (kernel == 4) return es == 8 ? launch_r4_strip_t<4, double, 2, 8, true>(s) : launch_r4_strip_t<4, float, 2, 8, true>(s);
     return cudaErrorInvalidValue;
   }
@@ -104,10 +107,8 @@ cudaError_t launch_r4(int kernel, int es, const StreamLaunch &s) {
     if (s.tile == 8) return es == 8 ? launch_r4_t<0, double, 8>(s) : launch_r4_t<0, float, 8>(s);
     if (s.tile == 16) return es == 8 ? launch_r4_t<0, double, 16>(s) : launch_r4_t<0, float, 16>(s);
     if (s.tile == 116) return es == 8 ? launch_r4_async_t<0, double, 16>(s) : launch_r4_async_t<0, float, 16>(s);
-    // 2 rows per thread (the strip kernel of slot 4): fewer shared-memory bytes and instructions per update
-    if (s.tile == 208) return es == 8 ? launch_r4_strip_t<0, double, 2, 8>(s) : launch_r4_strip_t<0, float, 2, 8>(s);
-    if (s.tile == 216) return es == 8 ? launch_r4_strip_t<0, double, 2, 16>(s) : launch_r4_strip_t<0, float, 2, 16>(s);
-    return es == 8 ? launch_r4_async_t<0, double, 8>(s) : launch_r4_async_t<0, float, 8>(s);
+    if (s.tile == 108) return es == 8 ? launch_r4_async_t<0, double, 8>(s) : launch_r4_async_t<0, float, 8>(s);
+    return es == 8 ? launch_r4_async_t<0, double, 16>(s) : launch_r4_async_t<0, float, 16>(s);
   }
   if (kernel == 4) {
     if (s.tile == 16) return es == 8 ? launch_r4_t<4, double, 16>(s) : launch_r4_t<4, float, 16>(s);
