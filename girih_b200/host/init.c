@@ -322,18 +322,35 @@ void gpu_attach(Parameters *p) {
   }
   gpu_check(p, girih_gpu_set_option(p->gpu, "variant", p->gpu_variant), "girih_gpu_set_option");
   gpu_check(p, girih_gpu_set_option(p->gpu, "overlap", p->gpu_overlap), "girih_gpu_set_option");
-  if ((p->gpu_push || p->gpu_copy) && p->mpi_size > 1 && p->t.shape[0] == 1 && p->t.shape[1] == 1) {
-    /* every rank thread maps its z neighbours' arrays (one process: peer access) */
-    unsigned char mine[GIRIH_PEER_BLOB_BYTES];
-    unsigned char *all = (unsigned char *)malloc((size_t)p->mpi_size * GIRIH_PEER_BLOB_BYTES);
-    gpu_check(p, girih_gpu_peer_export(p->gpu, mine, sizeof(mine)), "girih_gpu_peer_export");
-    team_allgather(mine, sizeof(mine), all, p->mpi_rank);
-    if (p->mpi_rank > 0)
-      gpu_check(p, girih_gpu_peer_attach(p->gpu, 0, all + (size_t)(p->mpi_rank - 1) * GIRIH_PEER_BLOB_BYTES, GIRIH_PEER_BLOB_BYTES), "girih_gpu_peer_attach");
-    if (p->mpi_rank + 1 < p->mpi_size)
-      gpu_check(p, girih_gpu_peer_attach(p->gpu, 1, all + (size_t)(p->mpi_rank + 1) * GIRIH_PEER_BLOB_BYTES, GIRIH_PEER_BLOB_BYTES), "girih_gpu_peer_attach");
-    free(all);
-    gpu_check(p, girih_gpu_set_option(p->gpu, p->gpu_copy ? "halo_copy" : "halo_push", 1), "girih_gpu_set_option");
+  {
+    /* halo copy / halo push: every rank thread maps its z neighbours' arrays (one process: peer access).  --gpu-copy is
+     * on by default (-1) for the halo-first and Diamond steppers; if any GPU cannot map a neighbour the run falls back
+     * to the NCCL exchange on every rank -- unless the flag was given explicitly, then it is an error. */
+    const int zslabs = p->mpi_size > 1 && p->t.shape[0] == 1 && p->t.shape[1] == 1;
+    const int want_copy = p->gpu_copy > 0 || (p->gpu_copy < 0 && !p->gpu_push && p->target_ts >= 1);
+    if ((p->gpu_push || want_copy) && zslabs) {
+      unsigned char mine[GIRIH_PEER_BLOB_BYTES];
+      unsigned char *all = (unsigned char *)malloc((size_t)p->mpi_size * GIRIH_PEER_BLOB_BYTES);
+      double ok = 1.0, okmin = 1.0;
+      int rc1 = girih_gpu_peer_export(p->gpu, mine, sizeof(mine)), rc2 = GIRIH_OK, rc3 = GIRIH_OK;
+      if (rc1 != GIRIH_OK) memset(mine, 0, sizeof(mine));
+      team_allgather(mine, sizeof(mine), all, p->mpi_rank);
+      if (rc1 == GIRIH_OK && p->mpi_rank > 0)
+        rc2 = girih_gpu_peer_attach(p->gpu, 0, all + (size_t)(p->mpi_rank - 1) * GIRIH_PEER_BLOB_BYTES, GIRIH_PEER_BLOB_BYTES);
+      if (rc1 == GIRIH_OK && rc2 == GIRIH_OK && p->mpi_rank + 1 < p->mpi_size)
+        rc3 = girih_gpu_peer_attach(p->gpu, 1, all + (size_t)(p->mpi_rank + 1) * GIRIH_PEER_BLOB_BYTES, GIRIH_PEER_BLOB_BYTES);
+      free(all);
+      if (rc1 != GIRIH_OK || rc2 != GIRIH_OK || rc3 != GIRIH_OK) ok = 0.0;
+      team_reduce(&ok, NULL, &okmin, NULL, 1, p->mpi_rank);
+      team_bcast(&okmin, sizeof(okmin), 0, p->mpi_rank);
+      if (okmin > 0.5) {
+        gpu_check(p, girih_gpu_set_option(p->gpu, want_copy ? "halo_copy" : "halo_push", 1), "girih_gpu_set_option");
+      } else if (p->gpu_push || p->gpu_copy > 0) {
+        gpu_check(p, rc1 != GIRIH_OK ? rc1 : (rc2 != GIRIH_OK ? rc2 : (rc3 != GIRIH_OK ? rc3 : GIRIH_ERR_UNSUPPORTED)), "girih_gpu_peer_attach");
+      } else {
+        girih_gpu_peer_detach(p->gpu);   /* every rank: NCCL exchange */
+      }
+    }
   }
   gpu_check(p, girih_gpu_set_option(p->gpu, "contract", p->gpu_contract), "girih_gpu_set_option");
   gpu_check(p, girih_gpu_upload(p->gpu, p->U1, p->U2, p->U3, p->coef), "girih_gpu_upload");

@@ -48,7 +48,7 @@ void param_default(Parameters *p) {
   p->t.shape[0] = p->t.shape[1] = p->t.shape[2] = 1;
   p->gpu_overlap = 0;
   p->gpu_push = 0;
-  p->gpu_copy = 0;
+  p->gpu_copy = -1;   /* auto: on for --npz > 1 z-slab runs of the halo-first and Diamond steppers when the GPUs can map each other */
   p->gpu_contract = 0;
   p->gpu_tune = 0;
   for (i = 0; i < 11; i++) p->g_coef[i] = (real_t)coef[i];
@@ -113,7 +113,7 @@ void print_help(Parameters *p) {
         "  --gpu-variant <int>\n       0 streamed kernels (default), 1 naive kernels\n"
         "  --gpu-tune <bool>\n       Measure every fusion depth and tile shape of the selected operator on the device before the\n       run and use the fastest (printed under [AUTO TUNE]; default 0 = built-in defaults)\n"
         "  --gpu-contract <bool>\n       Evaluate the stencil with the fused multiply-adds gcc emits for the reference under -O3 -mfma\n       (bit-identical to the reference built that way; default 0 = no FMA, bit-identical to the\n       reference's -O0 verifier).  --verify then passes on relative Linf <= 1e-12 (fp64) / 1e-5 (fp32)\n"
-        "  --gpu-copy <bool>\n       --npz > 1: outer parts of every slab first, then the halos travel into the neighbouring GPUs' halo planes by\n       copy engine (peer memory) under the sweep of the inner part\n"
+        "  --gpu-copy <bool>\n       --npz > 1: outer parts of every slab first, then the halos travel into the neighbouring GPUs' halo planes by\n       copy engine (peer memory) under the sweep of the inner part (default: on for --target-ts 1 and 2 when the GPUs\n       can map each other's memory, else the NCCL exchange)\n"
         "  --gpu-push <bool>\n       Diamond stepper, --npz > 1, 7-point constant operator: the fused sweep stores its boundary planes\n       straight into the neighbouring GPUs' halos over NVLink (no exchange between passes)\n"
         "  --gpu-overlap <bool>\n       Diamond stepper: compute the slab boundaries first and overlap the deep-halo exchange\n       with the interior (default 0: one blocking exchange per fused pass measured faster)\n"
         "  --z-mpi-contig <bool>  --halo-concatenate <integer>  --thread-group-size <integer>\n"
