@@ -665,7 +665,12 @@ extern "C" int girih_gpu_peer_export(girih_gpu_ctx *c, void *blob, size_t len) {
   void *ptrs[3] = {c->dU[0], c->dU[1], c->d_flags};
   for (int i = 0; i < 3; ++i) {
     b.ptr[i] = (unsigned long long)(uintptr_t)ptrs[i];
-    CU(cudaIpcGetMemHandle(&b.h[i], ptrs[i]));
+    // the IPC handle only matters to importers in OTHER processes (rank threads of one process use the pointer): where
+    // the platform refuses to make one, the blob still serves same-process peers and a foreign importer fails in attach
+    if (cudaIpcGetMemHandle(&b.h[i], ptrs[i]) != cudaSuccess) {
+      (void)cudaGetLastError();
+      memset(&b.h[i], 0, sizeof(b.h[i]));
+    }
   }
   memset(blob, 0, len);
   memcpy(blob, &b, sizeof(b));
