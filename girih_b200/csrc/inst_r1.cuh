@@ -22,9 +22,19 @@ template <typename R> static inline ConstCoef<R> make_cc(const double (&cc)[5]) 
   return k;
 }
 
+// Per kernel instantiation and device: has the dynamic shared-memory limit been raised, how many CTAs fit an SM, how many
+// SMs are there.  Asked once instead of on every launch (the queries sat on the launch path of every pass).
+// Rank threads of one process may race on an entry; they all write the same values.
+template <int K, typename R, int T, int PY, int NW, int DBG> struct R1LaunchCache {
+  static inline bool attr_done[64] = {};
+  static inline int occ[64] = {};
+  static inline int nsm[64] = {};
+};
+
 template <int K, typename R, int T, int PY, int NW, int DBG = 0>
 static cudaError_t launch_r1_t(const StreamLaunch &s) {
   using Cfg = R1Cfg<R, T, PY, NW>;
+  using Cache = R1LaunchCache<K, R, T, PY, NW, DBG>;
   const DevGrid &g = s.g;
   R1Args<R> a;
   a.g = g;
@@ -41,17 +51,25 @@ static cudaError_t launch_r1_t(const StreamLaunch &s) {
   a.push_dn_below = s.push_dn ? s.push_dn_below : -0x7fffffff;
   const int ntx = (g.nx + Cfg::UX - 1) / Cfg::UX, nty = (g.ny + Cfg::UY - 1) / Cfg::UY;
   auto kfn = k_r1<K, R, T, PY, NW, DBG>;
-  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-  if (e != cudaSuccess) return e;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = dev & 63;
+  if (!Cache::attr_done[slot]) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    int occ = 1, nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, 32 * NW, Cfg::SMEM) != cudaSuccess || occ < 1) occ = 1;
+    Cache::occ[slot] = occ;
+    Cache::nsm[slot] = nsm;
+    Cache::attr_done[slot] = true;
+  }
   int zchunk = s.zchunk;
   if (zchunk <= 0) {
     // Split z into chunks so that the CTAs fill whole waves of the 148 SMs: every chunk pays 2T planes
     // of pipeline fill, every partially filled last wave idles SMs.  Minimise
     //   waves(ntiles * nch) * (ceil(nz / nch) + 2T).
-    int occ = 1, nsm = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, 32 * NW, Cfg::SMEM) != cudaSuccess || occ < 1) occ = 1;
+    const int occ = Cache::occ[slot], nsm = Cache::nsm[slot];
     // a second range of the same length doubles the CTAs per chunk row
     const int nz = s.ze0 - s.zb0, ntiles = ntx * nty * (s.ze1 > s.zb1 ? 2 : 1), slots = nsm * occ;
     long long best = -1;

@@ -236,6 +236,10 @@ k_r1(const R1Args<R> a) {
   // non-interior point (no pass-through code at all), FRAME = true for warps on the x/y frame and for
   // the few iterations of the first/last z chunk whose planes touch the z frame.  Both versions execute
   // exactly one __syncthreads per iteration, so the warps of a CTA may take different versions.
+  // (The warps then reach the barrier from different code addresses.  sm_70+ counts arrivals per barrier, not per
+  // instruction, and every thread of the CTA executes exactly one bar.sync 0 per iteration on either path; the test
+  // suite's emulator counts the same way, and `compute-sanitizer --tool synccheck` on the GPU suite's fused cases is
+  // clean -- profiles/r02_synccheck.log.)
   {
   // S[l][.] : three rotating register planes of level l.  In phase PH (= iteration mod 3)
   //   S[l][PH] = plane zc-1 ("B"), S[l][(PH+1)%3] = plane zc ("C"), S[l][(PH+2)%3] = plane zc+1 ("F")

@@ -457,6 +457,7 @@ k_r1x(const R1xArgs<R> a) {
         }
       }
     }
+    __syncwarp();      // lanes that had to wait for a slot rejoin here: the CTA barrier is reached by whole warps
     __syncthreads();
   };
 
