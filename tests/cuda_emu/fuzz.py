@@ -18,8 +18,8 @@ import girih_b200 as G  # noqa: E402
 from girih_b200 import lib as L  # noqa: E402
 from oracle import girih_oracle as O  # noqa: E402
 
-TILES_F = {1: (0, 216, 408, 312, 310, 316, 5408, 5216, 7408, 7216, 9408, 9216), 2: (0, 216, 408, 9216, 9408), 3: (0, 216, 408, 9216, 9408), 5: (0, 216, 408, 9216, 9408)}
-TILES_S = {0: (0, 8, 16, 116), 4: (0, 8, 16), 7: (0, 4), 1: (0, 108, 208, 404, 408), 2: (0, 108, 208, 404, 408),
+TILES_F = {1: (0, 216, 408, 312, 310, 316, 5408, 5216, 7408, 7216, 9408, 9216, 10408, 10216), 2: (0, 216, 408, 9216, 9408), 3: (0, 216, 408, 9216, 9408), 5: (0, 216, 408, 9216, 9408)}
+TILES_S = {0: (0, 8, 16, 108, 116), 4: (0, 8, 16), 7: (0, 4), 1: (0, 108, 208, 404, 408), 2: (0, 108, 208, 404, 408),
            3: (0, 108, 208, 404, 408), 5: (0, 108, 208, 404, 408)}
 
 
@@ -38,7 +38,7 @@ def fuzz_kernels(seed, seconds, max_cases=10 ** 9, log=print):
         if fused:
             T = rnd.randint(1, d.max_tfuse)
             tile, variant = rnd.choice(TILES_F[k]), 2
-            if contract and tile not in (0, 5408, 5216, 7408, 7216, 9408, 9216):
+            if contract and tile not in (0, 5408, 5216, 7408, 7216, 9408, 9216, 10408, 10216):
                 tile = 0
             nsteps = rnd.randint(1, 3 * T + 2)
             sizes = G.plan_fused_passes(nsteps, T)
@@ -105,8 +105,16 @@ def fuzz_library(seed, seconds, max_cases=10 ** 9, log=print):
         tf, overlap, group = rnd.randint(0, 4), rnd.choice([0, 0, 1]), rnd.choice([0, 1, 2, 3, 4])
         variant = rnd.choice([0, 0, 1, 2]) if d.r == 1 and k != 7 else rnd.choice([0, 1])
         zchunk, contract = rnd.choice([0, 0, 3, 7]), rnd.random() < 0.25
+        # round 2: halo exchange through mapped peer memory (copy engines / push stores), exact tiles, z wavefront
+        peer = "" if (xy or nr == 1) else rnd.choice(["", "", "halo_copy", "halo_copy", "halo_push"])
+        tile = rnd.choice([0, 0, 10408, 10216]) if (k == 1 and dt == np.float64) else 0
+        zwave = rnd.choice([0, 2, 3]) if (nr == 1 and d.max_tfuse == 1) else 0
+        reps = rnd.choice([1, 1, 2])
         what = (k, np.dtype(dt).name, gst, dims, nsteps, "fused" if fused else "single", "tfuse", tf, "overlap", overlap,
-                "group", group, "variant", variant, "zchunk", zchunk, "contract", contract)
+                "group", group, "variant", variant, "zchunk", zchunk, "contract", contract, "peer", peer, "tile", tile,
+                "zwave", zwave, "reps", reps)
+        blobs = [None] * nr
+        gate = threading.Barrier(nr)
         uid = EmuGpuStepper.comm_unique_id()
         out, errs = [None] * nr, []
 
@@ -117,18 +125,32 @@ def fuzz_library(seed, seconds, max_cases=10 ** 9, log=print):
                 s.set_topology(pb.dims, pb.coords)
                 s.comm_init(uid)
                 for key, v in (("overlap", overlap), ("halo_group", group), ("variant", variant), ("zchunk", zchunk),
-                               ("contract", int(contract))):
+                               ("contract", int(contract)), ("tile", tile), ("zwave", zwave), ("zwave_block", 1 + zchunk)):
                     s.set_option(key, v)
+                if peer:
+                    blobs[rank] = s.peer_export()
+                    gate.wait()
+                    if rank > 0:
+                        s.peer_attach(0, blobs[rank - 1])
+                    if rank + 1 < nr:
+                        s.peer_attach(1, blobs[rank + 1])
+                    s.set_option(peer, 1)
                 s.upload(pb)
-                if fused:
-                    s.run_fused(nsteps, tf)
-                else:
-                    s.run_single(nsteps, overlap=bool(overlap))
+                if peer:
+                    gate.wait()
+                for _ in range(reps):
+                    if fused:
+                        s.run_fused(nsteps, tf)
+                    else:
+                        s.run_single(nsteps, overlap=bool(overlap))
                 s.download(pb.U1, pb.U2)
+                if peer:
+                    gate.wait()      # nobody unmaps while a neighbour may still write
                 s.close()
                 out[rank] = pb
             except Exception as e:   # noqa: BLE001
                 errs.append(e)
+                gate.abort()
 
         th = [threading.Thread(target=work, args=(q,)) for q in range(nr)]
         [t.start() for t in th]
@@ -142,7 +164,8 @@ def fuzz_library(seed, seconds, max_cases=10 ** 9, log=print):
             continue
         n += 1
         ob = O.make_problem(k, gst, dt)
-        O.run_steps(ob, nsteps, contract=contract)
+        for _ in range(reps):
+            O.run_steps(ob, nsteps, contract=contract)
         ok = True
         for pb in out:
             x0, y0, z0 = pb.gb
