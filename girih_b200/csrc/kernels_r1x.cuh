@@ -11,20 +11,23 @@
 //     all CTAs of the launch co-resident (cooperative launch); a CTA streams along z with the same
 //     register pipeline as k_r1 (three rotating register planes per fused level, level l+1 one plane
 //     behind level l)
-//   * what a tile is missing at its rim -- for every level l < T the column left / right of the tile and
+//   * what a tile is missing at its rim -- for every level 1 <= l < T the column left / right of the tile and
 //     the row above / below it, plane by plane -- is handed over by the neighbouring CTA as soon as it has
 //     produced it: the producer stores the values straight into the consumer's inbound slots in global
 //     memory (they live in L2), every 8-byte word carrying its own sequence tag (payload, tag) like
 //     NCCL's LL protocol, so there is no fence, no flag round trip and no barrier between CTAs; the
-//     consumer polls a slot until the tag of the iteration it needs shows up
+//     consumer polls a slot until the tag of the iteration it needs shows up.  Level 0 is the input array:
+//     its rim is read from global memory by every tile, like the frame cells of the tiles on the Dirichlet frame
 //   * a value is published in iteration g (stage l-1) and consumed in iteration g+1 (stage l): one whole
-//     iteration (~2300 cycles) of slack against an L2 round trip of ~600; slots are a ring of three
-//     generations, which the dependence chain makes sufficient (see DESIGN.md 4.2b)
-//   * polling is spread over the warps and over the T stages of an iteration, one 16-byte slot per lane
-//     in flight: the load is issued at the start of a stage and checked at its end, i.e. its latency
-//     runs under the stage's arithmetic
-//   * tiles on the Dirichlet frame read the frame cells (which no level changes) from the input array
-//     instead
+//     iteration of slack against a measured hand-over latency of 700-1050 cycles; slots are a ring of three
+//     generations, which the dependence chain makes sufficient (DESIGN.md 4.2b)
+//   * every poll is private to the consuming warp and issued in the stage before the one that needs the value
+//     (T-1 stages after the store), one 16-byte slot per lane in flight, checked after the stage's arithmetic
+//   * every store / load of the exchange in the hot block is a predicated instruction, not a branch (the T fused
+//     levels stay one basic block); rim columns are parked in shared memory by lanes 0 / 31 and leave with ONE
+//     store per warp and stage; the rows above / below leave with the first / last warp
+// Status: bit-exact (GPU + emulator), NOT a performance path -- 0.60 ms per pass without the exchange (889 GLUP/s
+// at 512^3) but 2.3-3.4 ms with it; the cost of each part is in profiles/r02_exact_tiles_analysis.md.
 //
 // fp64 only (one value + tags = one 16-byte slot).
 #pragma once
