@@ -77,6 +77,7 @@ test_naive_variant_and_edge_sizes = P.test_naive_variant_and_edge_sizes
 test_step_box_is_the_operator_contract = P.test_step_box_is_the_operator_contract
 test_repeated_runs_keep_evolving_like_the_reference = P.test_repeated_runs_keep_evolving_like_the_reference
 test_frame_mismatch_is_reported = P.test_frame_mismatch_is_reported
+test_frame_mismatch_after_field_only_uploads_is_reported = P.test_frame_mismatch_after_field_only_uploads_is_reported
 test_scan_counts_nan_and_zero = P.test_scan_counts_nan_and_zero
 test_z_slabs_match_global_oracle = P.test_z_slabs_match_global_oracle
 test_xy_topologies_match_global_oracle = P.test_xy_topologies_match_global_oracle
