@@ -32,11 +32,38 @@ static cudaError_t launch_box_t(const StreamLaunch &s) {
   return cudaGetLastError();
 }
 
-// tile option = warps (rows) per CTA: 4 or 8 (default)
+template <typename R, int NW, bool FM>
+static cudaError_t launch_box_async_t(const StreamLaunch &s) {
+  using Cfg = BoxACfg<R, NW>;
+  const DevGrid &g = s.g;
+  BoxArgs<R> a;
+  a.g = g;
+  a.in = (const R *)s.in;
+  a.out = (R *)s.out;
+  for (int i = 0; i < 5; ++i) a.cc.v[i] = (R)s.cc[i];
+  a.zb0 = s.zb0;
+  a.ze0 = s.ze0;
+  const int nz = s.ze0 - s.zb0;
+  int zchunk = s.zchunk > 0 ? s.zchunk : 64;
+  zchunk = std::min(zchunk, std::max(nz, 1));
+  a.zchunk = zchunk;
+  dim3 grid((g.nx + Cfg::WX - 1) / Cfg::WX, (g.ny + NW - 1) / NW, (nz + zchunk - 1) / zchunk);
+  auto kfn = k_box_async<R, NW, FM>;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  if (e != cudaSuccess) return e;
+  GIRIH_LAUNCH(kfn, grid, 32 * NW, Cfg::SMEM, s.stream, a);
+  return cudaGetLastError();
+}
+
+// tile option: 4 / 8 = the register-marching kernel with that many rows per CTA, 108 / 116 = the cp.async kernel with 8 / 16
+// rows; default = cp.async, 8 rows (round 2, 512^3 sustained: fp64 240 against 164 GLUP/s, fp32 492-511 against 397-412;
+// profiles/r02_box_async.log)
 cudaError_t launch_box(int es, const StreamLaunch &s) {
-  if (s.contract) return es == 8 ? launch_box_t<double, 8, true>(s) : launch_box_t<float, 8, true>(s);
+  if (s.contract) return es == 8 ? launch_box_async_t<double, 8, true>(s) : launch_box_async_t<float, 8, true>(s);
   if (s.tile == 4) return es == 8 ? launch_box_t<double, 4, false>(s) : launch_box_t<float, 4, false>(s);
-  return es == 8 ? launch_box_t<double, 8, false>(s) : launch_box_t<float, 8, false>(s);
+  if (s.tile == 8) return es == 8 ? launch_box_t<double, 8, false>(s) : launch_box_t<float, 8, false>(s);
+  if (s.tile == 116) return es == 8 ? launch_box_async_t<double, 16, false>(s) : launch_box_async_t<float, 16, false>(s);
+  return es == 8 ? launch_box_async_t<double, 8, false>(s) : launch_box_async_t<float, 8, false>(s);
 }
 
 }  // namespace girih

@@ -15,6 +15,7 @@
 // "contract" option): at 512^3 fp64 the FP64 pipe and HBM need about the same time.
 #pragma once
 #include "common.cuh"
+#include "kernels_r4.cuh"   // cp_async16 / cp_async_commit / cp_async_wait
 #include "stencil_expr.cuh"
 
 namespace girih {
@@ -136,6 +137,168 @@ k_box_march(const BoxArgs<R> a) {
   if (z < ze) { body(BPhase<0>{}, z); ++z; }
   if (z < ze) { body(BPhase<1>{}, z); ++z; }
   if (z < ze) { body(BPhase<2>{}, z); }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_box_async (round 2) -- the same operator with the plane stream prefetched by cp.async into a 4-stage
+// shared-memory ring, the schedule of k_r4_async.  k_box_march keeps ONE plane in flight per thread and reads
+// every row three times through L1: 8 KB of new bytes in flight per SM, spills of in-flight load destinations at
+// the 128-register cap, 40-47% of the HBM roofline (ncu: long scoreboard 5 cycles per issue).  Here
+//   * the CTA tile is WX x NW points (one row per warp); every plane of the tile, with its one-point rim in x
+//     and y, is staged in shared memory: one 16-byte cp.async per thread for its own points, one more for a
+//     rim item (rows -1 / NW as vectors, the rim columns as single elements), one commit group per plane,
+//     THREE planes in flight at no register cost (24 KB per CTA in fp64)
+//   * a plane is read from shared memory ONCE, when it becomes plane z+1 of the thread's column: its rows
+//     y-1, y, y+1 with the element left and right of them (9 loads) go into the register ring that already
+//     holds the planes z-1 and z
+//   * one __syncthreads per plane; tiles do not overlap
+// ------------------------------------------------------------------------------------------------------
+#ifndef GIRIH_CUDA_EMU
+template <int BYTES> __device__ __forceinline__ void cp_async_small(void *smem, const void *gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(gmem), "n"(BYTES) : "memory");
+}
+#endif   // the test suite's CPU SIMT emulator supplies its own version
+
+template <typename R, int NW> struct BoxACfg {
+  static constexpr int VX = Vec<R>::N;
+  static constexpr int WX = 32 * VX;
+  static constexpr int NT = 32 * NW;
+  static constexpr int NS = 4;                       // stages: the plane being read + 3 in flight
+  static constexpr int PAD = VX;                     // the rim column left of the tile sits at PAD - 1 (rows stay 16-byte aligned)
+  static constexpr int SP = WX + 2 * PAD;            // shared row pitch (elements)
+  static constexpr int SROWS = NW + 2;
+  static constexpr int PLANE = SROWS * SP;
+  static constexpr int NRIM = 2 * 32 + 2 * SROWS;    // rim items of a plane: 2 rows of 32 vectors, 2 columns of SROWS elements
+  static constexpr size_t SMEM = (size_t)NS * PLANE * sizeof(R);
+  static_assert(NRIM <= NT, "one rim item per thread");
+};
+
+template <typename R, int NW, bool FM = false>
+__global__ void __launch_bounds__(32 * NW)
+k_box_async(const BoxArgs<R> a) {
+  using Cfg = BoxACfg<R, NW>;
+  constexpr int VX = Cfg::VX, WX = Cfg::WX, NS = Cfg::NS, PAD = Cfg::PAD, SP = Cfg::SP, PLANE = Cfg::PLANE;
+  constexpr int SROWS = Cfg::SROWS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  R *planes = reinterpret_cast<R *>(smem_raw);       // [NS][SROWS][SP]
+
+  const DevGrid &g = a.g;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x0t = g.X0 + (int)blockIdx.x * WX, y0t = g.Y0 + (int)blockIdx.y * NW;
+  const int x = x0t + lane * VX, y = y0t + warp;
+  const int zb = a.zb0 + (int)blockIdx.z * a.zchunk;
+  const int ze = min(zb + a.zchunk, a.ze0);
+  const bool ok = (x + VX <= g.px) && (y < g.ny_dev);        // my vector may be loaded
+  unsigned inter = 0;
+#pragma unroll
+  for (int e = 0; e < VX; ++e)
+    if ((x + e < g.X0 + g.nx) && (y < g.Y0 + g.ny)) inter |= 1u << e;
+  const long long off = (long long)y * g.px + x;
+
+  // my rim item of a plane: tid < 64: a vector of row -1 / NW; then the elements left / right of rows -1 .. NW
+  int rim_s = 0, rim_kind = 0;       // 0 none, 1 vector, 2 single element
+  long long rim_g = 0;
+  if (tid < 64) {
+    const int srow = (tid < 32) ? 0 : SROWS - 1, vv = tid & 31;
+    const int gx = x0t + vv * VX, gy = y0t - 1 + srow;
+    rim_s = srow * SP + PAD + vv * VX;
+    rim_g = (long long)gy * g.px + gx;
+    rim_kind = (gx + VX <= g.px && gy >= 0 && gy < g.ny_dev) ? 1 : 0;
+  } else if (tid < Cfg::NRIM) {
+    const int k = tid - 64, srow = k >> 1, side = k & 1;
+    const int gx = side == 0 ? x0t - 1 : x0t + WX, gy = y0t - 1 + srow;
+    rim_s = srow * SP + (side == 0 ? PAD - 1 : PAD + WX);
+    rim_g = (long long)gy * g.px + gx;
+    rim_kind = (gx >= 0 && gx < g.px && gy >= 0 && gy < g.ny_dev) ? 2 : 0;
+  }
+  // G(p): plane p of the tile and its rim, one commit group (possibly empty past the chunk)
+  auto issue_group = [&](int p) {
+    if (p <= ze && p >= 0 && p < g.nz_dev) {
+      R *buf = planes + (size_t)((p - zb) & (NS - 1)) * PLANE;
+      const R *pv = a.in + (long long)p * g.pxy;
+      if (ok) cp_async16(buf + (1 + warp) * SP + PAD + lane * VX, pv + off);
+      if (rim_kind == 1) cp_async16(buf + rim_s, pv + rim_g);
+      else if (rim_kind == 2) cp_async_small<(int)sizeof(R)>(buf + rim_s, pv + rim_g);
+    }
+    cp_async_commit();
+  };
+
+  R ctr[3][3][VX];   // ctr[(ph + i) % 3][row] = my points of plane z-1+i, rows y-1, y, y+1
+  R lr[3][3][2];     // element left / right of them
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int e = 0; e < VX; ++e) ctr[i][r][e] = (R)0;
+      lr[i][r][0] = lr[i][r][1] = (R)0;
+    }
+  // a staged plane -> my three rows and their side elements
+  auto take = [&](const R *s, R (&c)[3][VX], R (&d)[3][2]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const R *row = s + (warp + r) * SP + PAD + lane * VX;
+      ld128s<R>(row, c[r]);
+      d[r][0] = row[-1];
+      d[r][1] = row[VX];
+    }
+  };
+  static_assert(NS == 4, "stage index uses a mask");
+  // prologue: planes zb-1 and zb go through the ring too (stages 3 and 0); then zb+1, zb+2, zb+3 are in flight
+  issue_group(zb - 1);
+  issue_group(zb);
+  issue_group(zb + 1);
+  issue_group(zb + 2);
+  cp_async_wait<2>();
+  __syncthreads();
+  take(planes + (size_t)(NS - 1) * PLANE, ctr[0], lr[0]);
+  take(planes + (size_t)0 * PLANE, ctr[1], lr[1]);
+  __syncthreads();                                   // everyone has taken plane zb-1: its stage may be refilled
+  issue_group(zb + 3);
+
+  auto body = [&](auto phase_tag, const int z) {
+    constexpr int PH = decltype(phase_tag)::value;
+    constexpr int S0 = PH % 3, S1 = (PH + 1) % 3, S2 = (PH + 2) % 3;
+    cp_async_wait<2>();                              // G(z+1) has landed (for this thread); z+2, z+3 may be in flight
+    __syncthreads();                                 // ... for everyone; and everyone has left iteration z-1
+    issue_group(z + 4);                              // refills the stage of plane z, taken in iteration z-1
+    take(planes + (size_t)((z + 1 - zb) & (NS - 1)) * PLANE, ctr[S2], lr[S2]);
+    R o[VX];
+#pragma unroll
+    for (int e = 0; e < VX; ++e) {
+      BoxNb<R> n;
+#pragma unroll
+      for (int dz = 0; dz < 3; ++dz) {
+        const int s = (dz == 0) ? S0 : (dz == 1) ? S1 : S2;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          n.v[dz][r][0] = (e > 0) ? ctr[s][r][e > 0 ? e - 1 : 0] : lr[s][r][0];
+          n.v[dz][r][1] = ctr[s][r][e];
+          n.v[dz][r][2] = (e < VX - 1) ? ctr[s][r][e < VX - 1 ? e + 1 : 0] : lr[s][r][1];
+        }
+      }
+      o[e] = StencilExpr<7>::template eval<R, FM>(n, a.cc, (R)0, (R)0);
+    }
+    R *q = a.out + off + (long long)z * g.pxy;
+    if (inter == (1u << VX) - 1u) {
+      st128<R>(q, o);
+    } else if (inter != 0u) {
+#pragma unroll
+      for (int e = 0; e < VX; ++e)
+        if ((inter >> e) & 1u) q[e] = o[e];
+    }
+  };
+
+  int z = zb;
+  for (; z + 3 <= ze; z += 3) {
+    body(BPhase<0>{}, z);
+    body(BPhase<1>{}, z + 1);
+    body(BPhase<2>{}, z + 2);
+  }
+  if (z < ze) { body(BPhase<0>{}, z); ++z; }
+  if (z < ze) { body(BPhase<1>{}, z); }
+  cp_async_wait<0>();
 }
 
 }  // namespace girih

@@ -137,13 +137,13 @@ unsigned long long warp_exchange(unsigned long long v, int src_lane) {
   return w.buf[slot][src_lane];
 }
 
-void cp_async_issue(void *dst, const void *src) {
+void cp_async_issue(void *dst, const void *src, int bytes) {
   Thread *t = TH;
   if (t->qn == t->qcap) {
     t->qcap = t->qcap ? 2 * t->qcap : 64;
     t->q = (Thread::Copy *)realloc(t->q, sizeof(Thread::Copy) * (size_t)t->qcap);
   }
-  t->q[t->qn++] = Thread::Copy{dst, src};
+  t->q[t->qn++] = Thread::Copy{dst, src, bytes};
 }
 void cp_async_commit_group() {
   Thread *t = TH;
@@ -157,7 +157,7 @@ void cp_async_wait_group(int n) {
   if (t->ngroups <= n) return;
   const int ndone = t->ngroups - n;
   const int upto = t->gend[ndone - 1];
-  for (int i = 0; i < upto; ++i) memcpy(t->q[i].dst, t->q[i].src, 16);
+  for (int i = 0; i < upto; ++i) memcpy(t->q[i].dst, t->q[i].src, (size_t)t->q[i].bytes);
   memmove(t->q, t->q + upto, sizeof(Thread::Copy) * (size_t)(t->qn - upto));
   t->qn -= upto;
   for (int g = ndone; g < t->ngroups; ++g) t->gend[g - ndone] = t->gend[g] - upto;

@@ -19,7 +19,7 @@ from girih_b200 import lib as L  # noqa: E402
 from oracle import girih_oracle as O  # noqa: E402
 
 TILES_F = {1: (0, 216, 408, 312, 310, 316, 5408, 5216, 7408, 7216, 9408, 9216, 10408, 10216), 2: (0, 216, 408, 9216, 9408), 3: (0, 216, 408, 9216, 9408), 5: (0, 216, 408, 9216, 9408)}
-TILES_S = {0: (0, 8, 16, 108, 116), 4: (0, 8, 16), 7: (0, 4), 1: (0, 108, 208, 404, 408), 2: (0, 108, 208, 404, 408),
+TILES_S = {0: (0, 8, 16, 108, 116), 4: (0, 8, 16), 7: (0, 4, 8, 116), 1: (0, 108, 208, 404, 408), 2: (0, 108, 208, 404, 408),
            3: (0, 108, 208, 404, 408), 5: (0, 108, 208, 404, 408)}
 
 

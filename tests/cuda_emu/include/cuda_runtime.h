@@ -56,7 +56,7 @@ struct Thread {
   bool done;
   unsigned ncoll;    // warp collectives executed so far
   // cp.async: copies of committed groups that have not been waited for yet
-  struct Copy { void *dst; const void *src; };
+  struct Copy { void *dst; const void *src; int bytes; };
   Copy *q;
   int qcap, qn;            // copies queued (all groups)
   int gend[16], ngroups;   // end index of each committed group (FIFO)
@@ -89,7 +89,7 @@ void launch_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()>
 // cooperative launch: every CTA of the grid runs at the same time (one OS thread per CTA), so CTAs may wait for each other
 void launch_coop_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()> &entry);
 void coop_pause();   // inside a spin on another CTA's progress: lets the other fibers of this CTA and the other CTAs run
-void cp_async_issue(void *dst, const void *src);
+void cp_async_issue(void *dst, const void *src, int bytes = 16);
 void cp_async_commit_group();
 void cp_async_wait_group(int n);
 
@@ -304,6 +304,7 @@ static inline void sb_wait(unsigned long long *bar, unsigned parity) {
   while ((unsigned)((*(volatile unsigned long long *)bar) >> 32 & 1u) == parity) cuda_emu::yield();
 }
 static inline void cp_async16(void *smem, const void *gmem) { cuda_emu::cp_async_issue(smem, gmem); }
+template <int BYTES> static inline void cp_async_small(void *smem, const void *gmem) { cuda_emu::cp_async_issue(smem, gmem, BYTES); }
 static inline void cp_async_commit() { cuda_emu::cp_async_commit_group(); }
 template <int N> static inline void cp_async_wait() { cuda_emu::cp_async_wait_group(N); }
 }  // namespace girih
