@@ -639,6 +639,20 @@ struct PeerBlob {
 };
 static_assert(sizeof(PeerBlob) <= GIRIH_PEER_BLOB_BYTES, "blob size");
 
+// How long a one-thread wait kernel polls its neighbours' flags before it gives up and the run reports an error instead of
+// hanging: 60 s of device clock by default (a neighbour may be busy with a first-launch module load, an upload or the tuner),
+// GIRIH_FLAG_TIMEOUT_S overrides it (the fixed ~10 s limit could fire spuriously).
+static long long flag_wait_cycles() {
+  static long long cycles = 0;
+  if (cycles == 0) {
+    const char *e = getenv("GIRIH_FLAG_TIMEOUT_S");
+    double sec = e ? atof(e) : 60.0;
+    if (!(sec > 0.0)) sec = 60.0;
+    cycles = (long long)(sec * 2.0e9);
+  }
+  return cycles;
+}
+
 __global__ void k_flag_signal(volatile int *dn_slot, volatile int *up_slot, int v) {
   __threadfence_system();   // the sweep's stores into peer memory are ordered before the flag
   if (dn_slot) *dn_slot = v;
@@ -1224,7 +1238,7 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
       // both neighbours have passed their last signal (end of pass p-1, or of the initial exchange): their stores
       // into my halos are complete and they no longer read the halo planes this pass overwrites
       GIRIH_LAUNCH(k_flag_wait, 1, 1, 0, c->s_comp, (volatile int *)c->d_flags, (int)need_dn, (int)need_up, c->push_seq,
-                   20000000000LL);
+                   flag_wait_cycles());
       CU(cudaGetLastError());
       c->n_kernels++;
       c->push_planes = (p + 1 < sizes.size()) ? sizes[p + 1] * r : 0;   // what the next pass reads beyond its slab
@@ -1259,7 +1273,7 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
     if (copy_live) {
       // the halos of `src` were copied in by the neighbours during their previous pass: wait for both flags
       const bool wdn = neighbour(c, 2, -1) >= 0, wup = neighbour(c, 2, +1) >= 0;
-      GIRIH_LAUNCH(k_flag_wait, 1, 1, 0, c->s_comp, (volatile int *)c->d_flags, (int)wdn, (int)wup, c->push_seq, 20000000000LL);
+      GIRIH_LAUNCH(k_flag_wait, 1, 1, 0, c->s_comp, (volatile int *)c->d_flags, (int)wdn, (int)wup, c->push_seq, flag_wait_cycles());
       CU(cudaGetLastError());
       c->n_kernels++;
       copy_live = false;
