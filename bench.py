@@ -488,7 +488,7 @@ def main_ours(args):
     if args.e2e_mode == "pipelined":
         ins = [pb.U2, torch.from_numpy(pb.U2).clone().pin_memory().numpy()]          # two pinned input buffers
         outs = [out_u1, torch.empty(pb.U1.shape, dtype=torch.float64).pin_memory().numpy()]
-        e2e_steps = max(e2e_steps, min(args.steps, 16))   # the fill and drain of the pipeline are inside the timing
+        e2e_steps = max(e2e_steps, min(args.steps, 24))   # the fill and drain of the pipeline are inside the timing
     barrier()
     t0 = time.perf_counter()
     if args.e2e_mode == "pipelined":
