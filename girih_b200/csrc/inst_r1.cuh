@@ -239,6 +239,8 @@ static cudaError_t launch_r1_tile(const StreamLaunch &s) {
   // strict arithmetic: 2 rows x 16 warps with the split barrier is the fastest tile at every fused depth
   // (T = 4: 0.892 vs 0.917 ms per pass at 512^3, T = 3: 0.700 vs 0.848, T = 2: 0.562 vs 0.648)
   if constexpr (K == 1 && sizeof(R) == 8 && T >= 2) return launch_r1_t<K, R, T, 2, 16, R1_SPLIT>(s);
+  // fp32 at depth 4: the same tile with the split barrier, 1 040 against 1 013 GLUP/s (depths 2 and 3: no gain)
+  if constexpr (K == 1 && sizeof(R) == 4 && T == 4) return launch_r1_t<K, R, T, 2, 16, R1_SPLIT>(s);
   // per-point coefficients at depth 2: the trapezoid skip (outer warps skip the last level and its coefficient loads) is
   // the fastest tile for every fp64 operator and for slot 5 in fp32 (profiles/r02_kbench_others.log)
   if constexpr (KTraits<K>::NCA > 0 && T == 2 && (sizeof(R) == 8 || K == 5)) return launch_r1_t<K, R, T, 2, 16, R1_TRAP>(s);
