@@ -455,19 +455,20 @@ def main_ours(args):
     if rank == 0:
         sampler.start()
     barrier()
-    dev_ms, comm_ms, launches = 0.0, 0.0, 0
+    dev_ms, comm_ms, comp_ms, launches = 0.0, 0.0, 0.0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         s.run_fused(nsteps, tf)
         el = s.elapsed_ms()
         dev_ms += el["total"]
         comm_ms += el["comm"]
+        comp_ms += el["compute"]
         launches += s.launch_info()["kernels"]
     barrier()
     wall = time.perf_counter() - t0
     per_rank_compute = None
-    if world > 1:   # who is waiting for whom: compute time per rank (total - exchange/wait), ms per step
-        mine = torch.tensor([(dev_ms - comm_ms) / args.steps], dtype=torch.float64, device="cuda")
+    if world > 1:   # who is waiting for whom: time inside the sweeps per rank (cudaEvent pairs around every launch), ms per step
+        mine = torch.tensor([comp_ms / args.steps], dtype=torch.float64, device="cuda")
         allv = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allv, mine)
         per_rank_compute = [float(v.item()) for v in allv]
