@@ -1281,11 +1281,15 @@ static int run_passes(girih_gpu_ctx *c, const std::vector<int> &sizes, int &cur,
     const int nd = (p + 1 < sizes.size()) ? sizes[p + 1] * r : r;   // halo depth the next pass needs
     // (decided on the thinnest slab of the run so that every rank takes the same branch: the two branches
     // exchange at different points)
-    if (overlap && c->nranks > 1 && c->nz_min >= 4 * nd) {
+    // halo copy: the outer parts must be at least T*r planes thick, so that the sweep of the inner part never reads a halo
+    // plane -- the neighbours' NEXT copies land in the halo planes of this pass's source array as soon as they have my
+    // flag, i.e. possibly while my inner sweep is still running (found by the emulator fuzzer on 4- and 9-plane slabs)
+    const int nq = copy ? std::max(nd, T * r) : nd;
+    if (overlap && c->nranks > 1 && c->nz_min >= 4 * nq) {
       // the two outer quarters of the slab first (one launch, full waves: thin boundary launches would pay
       // the 2T-plane pipeline fill for a few planes), then the halo exchange of the new level runs under
       // the sweep of the inner half
-      const int zq = std::max(nd, g.nz / 4);
+      const int zq = std::max(nq, g.nz / 4);
       const bool need_dn = neighbour(c, 2, -1) >= 0, need_up = neighbour(c, 2, +1) >= 0;
       CU(timed_pass(c, T, src, dst, zb, zb + zq, ze - zq, ze));
       CU(cudaEventRecord(c->ev_y, c->s_comp));

@@ -68,6 +68,7 @@ test_tiles_and_z_chunks = P.test_tiles_and_z_chunks
 test_schedule_variant_tiles = P.test_schedule_variant_tiles
 test_exact_tiles_match_oracle = P.test_exact_tiles_match_oracle
 test_halo_copy_matches_global_oracle = P.test_halo_copy_matches_global_oracle
+test_halo_copy_on_thin_slabs_matches_global_oracle = P.test_halo_copy_on_thin_slabs_matches_global_oracle
 test_z_wavefront_through_l2_matches_oracle = P.test_z_wavefront_through_l2_matches_oracle
 test_trapezoid_skip_variable_coefficients = P.test_trapezoid_skip_variable_coefficients
 test_marching_kernel_tiles = P.test_marching_kernel_tiles
