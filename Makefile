@@ -11,7 +11,7 @@ NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -
 CFLAGS    := -std=gnu99 -O2 -ffp-contract=off -fopenmp -fPIC -Wall -Wno-unknown-pragmas
 CSRC      := girih_b200/csrc
 HSRC      := girih_b200/host
-HOST_C    := $(HSRC)/params.c $(HSRC)/init.c $(HSRC)/steppers.c $(HSRC)/perf.c $(HSRC)/verify.c $(HSRC)/team.c $(HSRC)/pyapi.c
+HOST_C    := $(HSRC)/params.c $(HSRC)/init.c $(HSRC)/steppers.c $(HSRC)/perf.c $(HSRC)/verify.c $(HSRC)/solar.c $(HSRC)/team.c $(HSRC)/pyapi.c
 CUDA_DEPS := $(wildcard $(CSRC)/*.cu $(CSRC)/*.cuh $(CSRC)/*.h) include/girih_cuda.h
 LIB       := girih_b200/libgirih_cuda.so
 

@@ -302,6 +302,9 @@ def bench_configs(G, local, peak):
         ("C4 7pt-var-nosym fp64 512^3 x200 Diamond", 5, np.float64, 512, 200, 2, 3),
         ("C4 25pt-var-axsym fp64 512^3 x200", 4, np.float64, 512, 200, 0, 0),
         ("C5 25pt-const fp32 1024^3 x200 (1 GPU: the base of the strong-scaling runs at --gpus N)", 0, np.float32, 1024, 200, 1, 0),
+        # table slot 6: 12 complex fields + 28 complex coefficient arrays, 104 reals per cell and step
+        ("solar fp64 192^3 x50", 6, np.float64, 192, 50, 0, 0),
+        ("solar fp32 192^3 x50", 6, np.float32, 192, 50, 0, 0),
     ]
     for name, k, dt, n, nt, ts, td in cases:
         try:

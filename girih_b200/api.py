@@ -76,8 +76,8 @@ class HostProblem:
     r: int
     dims: tuple          # process topology (npx, npy, npz); z-slabs: (1, 1, nranks)
     coords: tuple        # this rank's position in it
-    U1: np.ndarray       # [nnz, nny, nnx]
-    U2: np.ndarray
+    U1: np.ndarray       # [nnz, nny, nnx]; solar slot: [12, nnz, nny, nnx, 2]
+    U2: np.ndarray | None  # None for the solar slot
     U3: np.ndarray | None
     coef: np.ndarray
 
@@ -99,6 +99,9 @@ def make_problem(kernel, gstencil, dtype=np.float64, rank=0, nranks=1, alignment
     dims = (1, 1, nranks) if topology is None else tuple(int(d) for d in topology)
     if dims[0] * dims[1] * dims[2] != nranks:
         raise ValueError("topology does not match nranks")
+    solar = kernel == 6   # 12 complex fields in ONE array [f][z][y][x][re, im], no U2, no x padding (src/utils.c:168-172, 359-361)
+    if solar:
+        padding = False
     ls, ds, gb, co = (C.c_int * 3)(), (C.c_int * 3)(), (C.c_int * 3)(), (C.c_int * 3)()
     h.girih_host_shapes_topo(kernel, _i3(gstencil), rank, _i3(dims), alignment, int(padding), ls, ds, gb, co)
     shape = tuple(ds)
@@ -112,11 +115,15 @@ def make_problem(kernel, gstencil, dtype=np.float64, rank=0, nranks=1, alignment
             return t.numpy()
         return np.empty(sh, dtype)
 
-    U1, U2 = alloc(zyx), alloc(zyx)
+    if solar:
+        U1, U2 = alloc((12,) + zyx + (2,)), None
+    else:
+        U1, U2 = alloc(zyx), alloc(zyx)
     U3 = alloc(zyx) if info.time_order == 2 else None
     coef = np.zeros(ncoef, dtype)
     rc = h.girih_host_fill_topo(kernel, _i3(gstencil), rank, _i3(dims), alignment, int(padding),
-                                U1.ctypes.data, U2.ctypes.data, U3.ctypes.data if U3 is not None else None,
+                                U1.ctypes.data, U2.ctypes.data if U2 is not None else None,
+                                U3.ctypes.data if U3 is not None else None,
                                 coef.ctypes.data)
     if rc:
         raise RuntimeError("girih_host_fill failed")
@@ -196,7 +203,7 @@ class GpuStepper:
         for a in (pb.U1, pb.U2, pb.U3, pb.coef):
             assert a is None or (a.dtype == self.dtype and a.flags.c_contiguous)
         self._check(self._lib.girih_gpu_upload(
-            self._ctx, pb.U1.ctypes.data, pb.U2.ctypes.data,
+            self._ctx, pb.U1.ctypes.data, pb.U2.ctypes.data if pb.U2 is not None else None,
             pb.U3.ctypes.data if pb.U3 is not None else None, pb.coef.ctypes.data), "girih_gpu_upload")
 
     def upload_fields(self, U1, U2):

@@ -37,7 +37,7 @@ static const girih_kernel_desc KERNELS[8] = {
     {"star", 1, 1, 6, GIRIH_STAR, GIRIH_COEF_VARIABLE_AXSYM, 4, 0, 6, 3, 1},
     {"star", 4, 1, 15, GIRIH_STAR, GIRIH_COEF_VARIABLE_AXSYM, 13, 0, 15, 1, 1},
     {"star", 1, 1, 9, GIRIH_STAR, GIRIH_COEF_VARIABLE_NOSYM, 7, 0, 9, 3, 1},
-    {"star", 1, 1, 40, GIRIH_STAR, GIRIH_COEF_SOLAR, 0, 0, 40, 1, 0},
+    {"star", 1, 1, 40, GIRIH_STAR, GIRIH_COEF_SOLAR, 0, 0, 104, 1, 1},   // solar: 28 complex arrays, not counted in nca
     {"box", 1, 1, 2, GIRIH_BOX, GIRIH_COEF_CONSTANT, 0, 4, 2, 1, 1},
 };
 
@@ -92,6 +92,10 @@ struct girih_gpu_ctx {
   std::vector<EvPair> comp_ev;        // one pair around every sweep of a run: "compute" is their sum, not total - comm
   size_t comp_ev_used = 0;
   bool uploaded = false, frames_equal = true, static_halo_done = false;
+  // slot 6 (solar): dU[0] holds the reference's ONE array of 12 complex fields, dCoef its 28 complex coefficient arrays,
+  // both in the host layout (no re-pitching); solar_n2 = reals per field = 2 * nnx * nny * nnz
+  bool solar = false;
+  long long solar_n2 = 0;
   bool frames_dirty = false;   // fields were replaced on the device since frames_equal was evaluated (upload_fields / commit_fields)
   unsigned long long *h_fflag = nullptr;   // page-locked, device-mapped word the frame check writes (no copy engine involved:
                                            // a D2H copy would queue behind the asynchronous download of the previous job)
@@ -189,6 +193,11 @@ extern "C" int girih_gpu_create(girih_gpu_ctx **out, int device, int target_kern
   if (elem_size != 4 && elem_size != 8) return GIRIH_ERR_ARG;
   if (!KERNELS[target_kernel].gpu_supported) return GIRIH_ERR_UNSUPPORTED;
   if (nranks < 1 || rank < 0 || rank >= nranks) return GIRIH_ERR_ARG;
+  const bool solar = KERNELS[target_kernel].coeff == GIRIH_COEF_SOLAR;
+  // solar: one rank (the reference's halo exchange moves U1 / U2 of one real per cell, src/mpi_utils.c:173-200, not the
+  // 12-field array) and no x padding (src/utils.c:359-361)
+  if (solar && nranks != 1) return GIRIH_ERR_UNSUPPORTED;
+  if (solar && ds[0] != st[0] + 2) return GIRIH_ERR_ARG;
   const int r = KERNELS[target_kernel].r;
   if (st[0] < 1 || st[1] < 1 || st[2] < 1) return GIRIH_ERR_ARG;
   if (ds[0] < st[0] + 2 * r || ds[1] != st[1] + 2 * r || ds[2] != st[2] + 2 * r) return GIRIH_ERR_ARG;
@@ -218,7 +227,13 @@ extern "C" int girih_gpu_create(girih_gpu_ctx **out, int device, int target_kern
 
   const size_t bytes = c->arr_elems * elem_size;
   cudaError_t e = cudaSuccess;
-  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+  c->solar = solar;
+  if (solar) {
+    c->solar_n2 = 2LL * ds[0] * ds[1] * ds[2];
+    e = cudaMalloc(&c->dU[0], (size_t)c->solar_n2 * 12 * elem_size);
+    if (e == cudaSuccess) e = cudaMalloc(&c->dCoef, (size_t)c->solar_n2 * 28 * elem_size);
+  }
+  for (int i = 0; i < 2 && e == cudaSuccess && !solar; ++i) {
     e = cudaMalloc(&c->dU[i], bytes);
     if (e == cudaSuccess) e = cudaMemset(c->dU[i], 0, bytes);
   }
@@ -370,7 +385,17 @@ static bool frames_match(const girih_gpu_ctx *c, const R *a, const R *b) {
 
 extern "C" int girih_gpu_upload(girih_gpu_ctx *c, const void *U1, const void *U2, const void *U3,
                                 const void *coef) {
-  if (!c || !U1 || !U2) return GIRIH_ERR_ARG;
+  if (!c || !U1) return GIRIH_ERR_ARG;
+  if (c->solar) {   // one field array (U2 == 0 in the reference, src/utils.c:171) and the coefficient arrays, layout unchanged
+    if (!coef) return fail(c, GIRIH_ERR_ARG, "coef is required");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(c->dU[0], U1, (size_t)c->solar_n2 * 12 * c->es, cudaMemcpyHostToDevice, c->s_comp));
+    CU(cudaMemcpyAsync(c->dCoef, coef, (size_t)c->solar_n2 * 28 * c->es, cudaMemcpyHostToDevice, c->s_comp));
+    CU(cudaStreamSynchronize(c->s_comp));
+    c->uploaded = true;
+    return GIRIH_OK;
+  }
+  if (!U2) return GIRIH_ERR_ARG;
   if (c->kd.time_order == 2 && !U3) return fail(c, GIRIH_ERR_ARG, "U3 (roc2) is required for time_order 2");
   if ((c->kd.n_coef_arrays > 0 || c->kd.n_coef_scalars > 0) && !coef) return fail(c, GIRIH_ERR_ARG, "coef is required");
   CU(cudaSetDevice(c->device));
@@ -452,6 +477,11 @@ static int fast_copy(girih_gpu_ctx *c, void *dev, void *host, bool to_device) {
 extern "C" int girih_gpu_upload_fields(girih_gpu_ctx *c, const void *U1, const void *U2) {
   if (!c || !c->uploaded) return fail(c, GIRIH_ERR_STATE, "upload_fields before upload");
   CU(cudaSetDevice(c->device));
+  if (c->solar) {
+    if (U1) CU(cudaMemcpyAsync(c->dU[0], U1, (size_t)c->solar_n2 * 12 * c->es, cudaMemcpyHostToDevice, c->s_comp));
+    CU(cudaStreamSynchronize(c->s_comp));
+    return GIRIH_OK;
+  }
   int rc;
   if (U1 && (rc = fast_copy(c, c->dU[0], const_cast<void *>(U1), true))) return rc;
   if (U2 && (rc = fast_copy(c, c->dU[1], const_cast<void *>(U2), true))) return rc;
@@ -512,6 +542,11 @@ extern "C" int girih_gpu_download(girih_gpu_ctx *c, void *U1, void *U2) {
   if (!c) return GIRIH_ERR_ARG;
   if (!c->uploaded) return fail(c, GIRIH_ERR_STATE, "download before upload");
   CU(cudaSetDevice(c->device));
+  if (c->solar) {
+    if (U1) CU(cudaMemcpyAsync(U1, c->dU[0], (size_t)c->solar_n2 * 12 * c->es, cudaMemcpyDeviceToHost, c->s_comp));
+    CU(cudaStreamSynchronize(c->s_comp));
+    return GIRIH_OK;
+  }
   int rc;
   if (U1 && (rc = fast_copy(c, c->dU[0], U1, false))) return rc;
   if (U2 && (rc = fast_copy(c, c->dU[1], U2, false))) return rc;
@@ -554,6 +589,7 @@ static cudaError_t launch_repitch(girih_gpu_ctx *c, void *dev, void *lin, bool t
 }
 
 extern "C" int girih_gpu_prefetch_fields(girih_gpu_ctx *c, const void *U1, const void *U2) {
+  if (c && c->solar) return fail(c, GIRIH_ERR_UNSUPPORTED, "pipelined transfers are not offered for the solar slot");
   if (!c || !c->uploaded) return fail(c, GIRIH_ERR_STATE, "prefetch_fields before upload");
   CU(cudaSetDevice(c->device));
   int rc = ensure_pipeline(c);
@@ -572,6 +608,7 @@ extern "C" int girih_gpu_prefetch_fields(girih_gpu_ctx *c, const void *U1, const
 }
 
 extern "C" int girih_gpu_commit_fields(girih_gpu_ctx *c) {
+  if (c && c->solar) return fail(c, GIRIH_ERR_UNSUPPORTED, "pipelined transfers are not offered for the solar slot");
   if (!c || !c->uploaded) return fail(c, GIRIH_ERR_STATE, "commit_fields before upload");
   if (!c->s_h2d) return fail(c, GIRIH_ERR_STATE, "commit_fields without prefetch_fields");
   CU(cudaSetDevice(c->device));
@@ -587,6 +624,7 @@ extern "C" int girih_gpu_commit_fields(girih_gpu_ctx *c) {
 }
 
 extern "C" int girih_gpu_download_async(girih_gpu_ctx *c, void *U1, void *U2) {
+  if (c && c->solar) return fail(c, GIRIH_ERR_UNSUPPORTED, "pipelined transfers are not offered for the solar slot");
   if (!c || !c->uploaded) return fail(c, GIRIH_ERR_STATE, "download before upload");
   CU(cudaSetDevice(c->device));
   int rc = ensure_pipeline(c);
@@ -1394,9 +1432,49 @@ static int finish_halos(girih_gpu_ctx *c) {
   return GIRIH_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// slot 6 (solar): a time step is the H update of every interior cell followed by the E update
+// (src/kernels/solar_spt_blk.ic:388-397), two launches on the compute stream
+// ------------------------------------------------------------------------------------------------
+static cudaError_t solar_step(girih_gpu_ctx *c, int xb, int yb, int zb, int xe, int ye, int ze, int phases) {
+  SolarLaunch s;
+  s.u = c->dU[0];
+  s.coef = c->dCoef;
+  s.n2 = c->solar_n2;
+  s.nnx = c->hshape[0]; s.nny = c->hshape[1];
+  s.xb = xb; s.xe = xe; s.yb = yb; s.ye = ye; s.zb = zb; s.ze = ze;
+  s.zchunk = c->opt_zchunk;
+  s.tile = c->opt_tile;
+  s.stream = c->s_comp;
+  for (int ph = 0; ph < 2; ++ph) {
+    if (!((phases >> ph) & 1)) continue;
+    cudaError_t e = launch_solar(c->es, ph, s);
+    if (e != cudaSuccess) return e;
+    c->n_kernels++;
+  }
+  return cudaSuccess;
+}
+static int solar_check(girih_gpu_ctx *c) {
+  if (c->opt_contract) return fail(c, GIRIH_ERR_UNSUPPORTED, "option contract is not offered for the solar slot");
+  return GIRIH_OK;
+}
+static int solar_run(girih_gpu_ctx *c, int nsteps) {
+  int rc;
+  if ((rc = solar_check(c))) return rc;
+  if ((rc = begin_run(c))) return rc;
+  for (int s = 0; s < nsteps; ++s) {
+    CU(solar_step(c, 1, 1, 1, c->hshape[0] - 1, c->hshape[1] - 1, c->hshape[2] - 1, 3));
+    c->n_passes++;
+    c->n_steps++;
+  }
+  c->tfuse_used = 1;
+  return end_run(c);
+}
+
 extern "C" int girih_gpu_run_single(girih_gpu_ctx *c, int nsteps, int overlap) {
   if (!c || nsteps < 0) return GIRIH_ERR_ARG;
   int rc;
+  if (c->solar) return solar_run(c, nsteps);
   if ((rc = begin_run(c))) return rc;
   if ((rc = exchange_static(c))) return rc;
   std::vector<int> sizes((size_t)nsteps, 1);
@@ -1452,6 +1530,8 @@ static int zwave_depth(const girih_gpu_ctx *c) {
 
 extern "C" int girih_gpu_run_fused(girih_gpu_ctx *c, int nsteps, int tfuse) {
   if (!c || nsteps < 0) return GIRIH_ERR_ARG;
+  // the reference's default wavefront (mwd_func_list, src/kernels/stencils.c:303-311) is not_supported_mwd for this slot
+  if (c->solar) return fail(c, GIRIH_ERR_UNSUPPORTED, "%s", girih_gpu_strerror(GIRIH_ERR_UNSUPPORTED));
   int T = tfuse;
   if (T <= 0) T = c->tuned_tfuse > 0 ? c->tuned_tfuse : default_tfuse(c);
   T = std::min(T, c->kd.max_tfuse);
@@ -1482,6 +1562,16 @@ extern "C" int girih_gpu_run_fused(girih_gpu_ctx *c, int nsteps, int tfuse) {
 extern "C" int girih_gpu_step_box(girih_gpu_ctx *c, int dst, int xb, int yb, int zb, int xe, int ye, int ze) {
   if (!c || (dst != 1 && dst != 2)) return GIRIH_ERR_ARG;
   if (!c->uploaded) return fail(c, GIRIH_ERR_STATE, "step_box before upload");
+  if (c->solar) {   // dst is ignored: the one array is updated in place (solar(), solar_spt_blk.ic:388-397, ALL_FIELDS)
+    if (xb < 1 || yb < 1 || zb < 1 || xe > c->hshape[0] - 1 || ye > c->hshape[1] - 1 || ze > c->hshape[2] - 1)
+      return fail(c, GIRIH_ERR_ARG, "box must lie inside the interior");
+    int rc = solar_check(c);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    CU(solar_step(c, xb, yb, zb, xe, ye, ze, 3));
+    CU(cudaStreamSynchronize(c->s_comp));
+    return GIRIH_OK;
+  }
   const DevGrid &g = c->g;
   const int r = g.r;
   if (xb < r || yb < r || zb < r || xe > g.nx + r || ye > g.ny + r || ze > g.nz + r)
@@ -1495,6 +1585,23 @@ extern "C" int girih_gpu_step_box(girih_gpu_ctx *c, int dst, int xb, int yb, int
 
 // `reps` passes of depth tfuse over this slab's interior planes, no halo exchange
 static int time_pass_local(girih_gpu_ctx *c, int tfuse, int reps, double *ms_per_pass) {
+  if (c->solar) {   // one pass = one time step (H + E)
+    int rc = solar_check(c);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    c->n_kernels = 0;
+    const int xe = c->hshape[0] - 1, ye = c->hshape[1] - 1, ze = c->hshape[2] - 1;
+    CU(solar_step(c, 1, 1, 1, xe, ye, ze, 3));   // warm
+    CU(cudaEventRecord(c->ev_t0, c->s_comp));
+    for (int i = 0; i < reps; ++i) CU(solar_step(c, 1, 1, 1, xe, ye, ze, 3));
+    CU(cudaEventRecord(c->ev_t1, c->s_comp));
+    CU(cudaStreamSynchronize(c->s_comp));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+    *ms_per_pass = (double)ms / reps;
+    c->tfuse_used = 1;
+    return GIRIH_OK;
+  }
   int T = std::max(1, std::min(tfuse, c->kd.max_tfuse));
   if (c->opt_variant == 1 || c->kernel == 7) T = 1;
   CU(cudaSetDevice(c->device));
@@ -1533,6 +1640,7 @@ extern "C" int girih_gpu_time_pass(girih_gpu_ctx *c, int tfuse, int reps, double
 // the caller uploads them again afterwards.
 // ------------------------------------------------------------------------------------------------
 static std::vector<int> tile_candidates(const girih_gpu_ctx *c, int T) {
+  if (c->solar) return {1, 2, 3, 4, 5};
   if (c->opt_variant == 1) return {0};
   if (c->kernel == 7) return {0, 4, 8, 116};
   if (c->kernel == 0) return {0, 8, 16, 108};
@@ -1651,11 +1759,48 @@ __global__ void k_scan(DevGrid g, const R *__restrict__ u, int hx, int hy, int h
   }
 }
 
+template <typename R>
+__global__ void k_scan_flat(const R *__restrict__ u, long long n, unsigned long long *out) {
+  unsigned long long nans = 0, zeros = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const R v = u[i];
+    nans += (v * (R)0 != (R)0) ? 1 : 0;
+    zeros += (fabs((double)v) < 1e-6) ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    nans += __shfl_down_sync(0xffffffffu, nans, o);
+    zeros += __shfl_down_sync(0xffffffffu, zeros, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (nans) atomicAdd(out, nans);
+    if (zeros) atomicAdd(out + 1, zeros);
+  }
+}
+
 extern "C" int girih_gpu_scan_u1(girih_gpu_ctx *c, uint64_t *n_nan_inf, uint64_t *n_zero) {
   if (!c) return GIRIH_ERR_ARG;
   if (!c->uploaded) return fail(c, GIRIH_ERR_STATE, "scan before upload");
   CU(cudaSetDevice(c->device));
   CU(cudaMemsetAsync(c->d_scan, 0, 2 * sizeof(unsigned long long), c->s_comp));
+  if (c->solar) {
+    // the reference scans the first ln_domain reals of the array (src/performance.c:131-141), i.e. the lower half of
+    // the first field: the same reals here (host layout on the device)
+    const long long n = c->solar_n2 / 2;
+    if (c->es == 8) {
+      auto kfn = k_scan_flat<double>;
+      GIRIH_LAUNCH(kfn, 148 * 8, 256, 0, c->s_comp, (const double *)c->dU[0], n, c->d_scan);
+    } else {
+      auto kfn = k_scan_flat<float>;
+      GIRIH_LAUNCH(kfn, 148 * 8, 256, 0, c->s_comp, (const float *)c->dU[0], n, c->d_scan);
+    }
+    CU(cudaGetLastError());
+    unsigned long long hs[2];
+    CU(cudaMemcpyAsync(hs, c->d_scan, sizeof(hs), cudaMemcpyDeviceToHost, c->s_comp));
+    CU(cudaStreamSynchronize(c->s_comp));
+    if (n_nan_inf) *n_nan_inf = hs[0];
+    if (n_zero) *n_zero = hs[1];
+    return GIRIH_OK;
+  }
   // the reference scans all ln_domain cells including the x padding, which is zero; count the
   // padding cells as zeros to report the same percentage
   const int hx = c->g.nx + 2 * c->g.r;

@@ -65,4 +65,18 @@ cudaError_t launch_r4(int kernel, int es, const StreamLaunch &a);
 // one step of the 27-point box operator (slot 7)
 cudaError_t launch_box(int es, const StreamLaunch &a);
 
+// one phase (0 = H update, 1 = E update; a time step is both, in that order) of the solar operator (slot 6) over a box
+// of cells of the reference's own array layout (12 complex fields in one array, 28 complex coefficient arrays)
+struct SolarLaunch {
+  void *u;
+  const void *coef;
+  long long n2;                   // 2 * nnx * nny * nnz: reals per field / coefficient array
+  int nnx, nny;
+  int xb, xe, yb, ye, zb, ze;     // cells [xb,xe) x [yb,ye) x [zb,ze), host-array coordinates
+  int zchunk;                     // 0 = choose
+  int tile;                       // 0 = default, 1..5 = schedule variants (inst_solar.cu)
+  cudaStream_t stream;
+};
+cudaError_t launch_solar(int es, int phase, const SolarLaunch &a);
+
 }  // namespace girih

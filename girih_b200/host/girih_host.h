@@ -121,6 +121,11 @@ void performance_test(Parameters *p);
 /* verify.c */
 void verify(Parameters *p);
 int verify_compute(Parameters *p, double *max_err, double *l1_err, double *max_ref);
+/* solar.c: table slot 6 (12 complex fields in one array, 28 complex coefficient arrays) */
+int is_solar(const Parameters *p);
+void solar_init_coeff(Parameters *p);
+void solar_domain_fill(Parameters *p);
+int solar_verify_compute(Parameters *p, double *max_err, double *l1_err, double *max_ref);
 
 /* team.c -- the ranks of one process */
 void team_init(int nranks);

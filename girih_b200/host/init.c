@@ -46,6 +46,15 @@ static void set_kernels(Parameters *p) { /* src/utils.c:253-262 */
   p->stencil.nd = d.nd;
   p->stencil.shape = d.shape;
   p->stencil.coeff = d.coeff;
+  if (d.coeff == GIRIH_COEF_SOLAR) {
+    /* the reference's default wavefront has no solar kernel (mwd_func_list, src/kernels/stencils.c:303-311:
+     * not_supported_mwd, src/kernels/stencils.h:40-43) and its halo exchange moves one real per cell */
+    if (p->target_ts == 2) {
+      if (p->mpi_rank == 0) printf("ERROR: unsupported configuration for the selected stencil\n");
+      exit(1);
+    }
+    if (p->mpi_size > 1) girih_fatal(p, "the solar kernel runs on one GPU (--npx 1 --npy 1 --npz 1)");
+  }
 }
 
 /* src/kernels/diamond_utils.c:850-1099, the parts that are not CPU thread/cache tuning */
@@ -135,6 +144,10 @@ void init(Parameters *p) { /* src/utils.c:317-433 */
   if (p->lstencil_shape[0] < 1 || p->lstencil_shape[1] < 1 || p->lstencil_shape[2] < 1)
     girih_fatal(p, "more GPUs than grid points along one direction");
 
+  if (is_solar(p) && p->array_padding == 1) { /* :359-361 */
+    if (p->mpi_rank == 0) fprintf(stdout, "WARNING: solar kernels do not support array padding\n");
+    p->array_padding = 0;
+  }
   if (p->array_padding == 1) { /* :367-374: alignment counts ELEMENTS here */
     if (p->alignment < 1) girih_fatal(p, "alignment must be positive");
     padding_comp = (p->lstencil_shape[0] + 2 * p->stencil.r) % p->alignment;
@@ -172,6 +185,7 @@ uint64_t coef_array_size(const Parameters *p) { /* src/utils.c:182-207 */
     case GIRIH_COEF_VARIABLE: return p->ln_domain * (uint64_t)(1 + p->stencil.r);
     case GIRIH_COEF_VARIABLE_AXSYM: return p->ln_domain * (uint64_t)(1 + 3 * p->stencil.r);
     case GIRIH_COEF_VARIABLE_NOSYM: return p->ln_domain * (uint64_t)(1 + 6 * p->stencil.r);
+    case GIRIH_COEF_SOLAR: return p->ln_domain * 28u * 2u;
     default: return 0;
   }
 }
@@ -189,6 +203,17 @@ static void *aligned_or_die(const Parameters *p, size_t bytes) {
 
 void arrays_allocate(Parameters *p) { /* src/utils.c:153-218 */
   const uint64_t coef_size = coef_array_size(p);
+  if (is_solar(p)) { /* :168-172: one array of 12 complex fields, U2 = 0 */
+    const uint64_t domain_size = p->ln_domain * 12u * 2u;
+    p->U1 = (real_t *)aligned_or_die(p, sizeof(real_t) * domain_size);
+    p->U2 = p->U3 = NULL;
+    p->coef = (real_t *)aligned_or_die(p, sizeof(real_t) * coef_size);
+    if (p->verbose == 1 && p->mpi_rank == 0)
+      printf("[rank=%d] alloc. dom(err=%d):%fGiB coef(err=%d):%fGiB total:%fGiB\n", p->mpi_rank, 0,
+             sizeof(real_t) * 1.0 * domain_size / (1024 * 1024 * 1024), 0, sizeof(real_t) * 1.0 * coef_size / (1024 * 1024 * 1024),
+             sizeof(real_t) * 1.0 * (coef_size + domain_size) / (1024 * 1024 * 1024));
+    return;
+  }
   p->U1 = (real_t *)aligned_or_die(p, sizeof(real_t) * p->ln_domain);
   p->U2 = (real_t *)aligned_or_die(p, sizeof(real_t) * p->ln_domain);
   p->U3 = NULL;
@@ -208,7 +233,7 @@ void arrays_allocate(Parameters *p) { /* src/utils.c:153-218 */
 void arrays_free(Parameters *p) { /* src/utils.c:220-245 */
   free(p->coef);
   free(p->U1);
-  free(p->U2);
+  free(p->U2); /* NULL for the solar slot */
   if (p->stencil.time_order == 2) free(p->U3);
   p->coef = p->U1 = p->U2 = p->U3 = NULL;
 }
@@ -218,6 +243,9 @@ void init_coeff(Parameters *p) { /* src/utils.c:436-481 */
   const uint64_t n = p->ln_domain;
   const int r = p->stencil.r;
   switch (p->stencil.coeff) {
+    case GIRIH_COEF_SOLAR: /* :483-489 */
+      solar_init_coeff(p);
+      break;
     case GIRIH_COEF_CONSTANT:
       for (i = 0; i < (uint64_t)r + 1; i++) p->coef[i] = p->g_coef[i];
       break;
@@ -252,6 +280,10 @@ void domain_data_fill(Parameters *p) { /* src/utils.c:605-697 */
   uint64_t n;
   int i, j, k, xb = 0, yb = 0, zb = 0;
   int xe = p->lstencil_shape[0] + 2 * r, ye = p->lstencil_shape[1] + 2 * r, ze = p->lstencil_shape[2] + 2 * r;
+  if (is_solar(p)) { /* :796-797 */
+    solar_domain_fill(p);
+    return;
+  }
   for (n = 0; n < p->ln_domain; n++) {
     p->U1[n] = 0.0;
     p->U2[n] = 0.0;

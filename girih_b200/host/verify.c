@@ -172,6 +172,7 @@ int verify_compute(Parameters *p, double *max_err, double *l1_err, double *max_r
   real_t *aggr;
   int i, j, k, rc, broken = 0;
 
+  if (is_solar(p)) return solar_verify_compute(p, max_err, l1_err, max_ref);
   arrays_allocate(p);
   init_coeff(p);
   domain_data_fill(p);

@@ -64,7 +64,7 @@ static const kinfo_t KINFO[8] = {
   {1, 1, 6,  COEF_AXSYM, 0},   /* 3 iso_ref_2space_1time_var_axsym   */
   {4, 1, 15, COEF_AXSYM, 0},   /* 4 iso_ref_8space_1time_var_axsym   */
   {1, 1, 9,  COEF_NOSYM, 0},   /* 5 iso_ref_2space_1time_var_nosym   */
-  {1, 1, 40, COEF_SOLAR, 0},   /* 6 solar (not restated: out of scope) */
+  {1, 1, 40, COEF_SOLAR, 0},   /* 6 solar: oracle_solar_* below       */
   {1, 1, 2,  COEF_CONST, 1},   /* 7 box_ref_2space_1time             */
 };
 
@@ -116,6 +116,7 @@ uint64_t oracle_coef_size(int k, uint64_t ln_domain)
     case COEF_VAR:   return ln_domain * (uint64_t)(1 + r);
     case COEF_AXSYM: return ln_domain * (uint64_t)(1 + 3 * r);
     case COEF_NOSYM: return ln_domain * (uint64_t)(1 + 6 * r);
+    case COEF_SOLAR: return ln_domain * 28u * 2u;                       /* utils.c:199-201 */
     default:         return 0;
   }
 }
@@ -377,4 +378,135 @@ int SFX(oracle_compare)(const real_t *ref, const real_t *target, int nx, int ny,
       }
   *max_err = maxe; *l1_err = diff_l1; *max_ref = mref;
   return ((diff_l1 > 0.0) || (diff_l1 * 0 != 0) || (diff_l1 != diff_l1)) ? 1 : 0;
+}
+
+
+/* ------------------------------------------------------------------------------------------
+ * Table slot 6, "solar": 12 complex field components (6 H, 6 E) in ONE array u of
+ * 12 x nnx*nny*nnz complex numbers (re, im interleaved; src/utils.c:168-172) and 28 complex
+ * coefficient arrays (src/utils.c:199-201).  One time step = the H update of every interior
+ * cell followed by the E update of every interior cell, in place
+ * (src/kernels/solar_spt_blk.ic:20-200 / :202-386 / :388-397; the serial verifier
+ * src/verification.c:481-784 holds the same expressions, character for character).
+ * Pinned like the rest: tests/test_oracle_vs_reference.py against oracle/_ref dumps and the
+ * committed fixtures.
+ * ------------------------------------------------------------------------------------------ */
+/* coefficients, src/utils.c:483-489: the flat index modulo 10 picks the value */
+void SFX(oracle_solar_init_coeff)(uint64_t ln_domain, real_t *coef)
+{
+  uint64_t i, n = ln_domain * 28u * 2u;
+  for (i = 0; i < n; i++) coef[i] = (real_t)G_COEF[i % 10];
+}
+
+/* fields, src/utils.c:698-727 (== the verifier's fill, src/verification.c:253-268, for gb = 0):
+ * every cell of the local array incl. its frame, no zero padding, no source planes */
+void SFX(oracle_solar_fill)(const int dshape[3], const int gstencil[3], const int gb[3], real_t *u)
+{
+  const int nnx = dshape[0], nny = dshape[1], nnz = dshape[2];
+  const uint64_t n = (uint64_t)nnx * nny * nnz;
+  int f, x, y, z;
+  for (f = 0; f < 12; f++)
+    for (z = 0; z < nnz; z++)
+      for (y = 0; y < nny; y++)
+        for (x = 0; x < nnx; x++) {
+          uint64_t gi = (uint64_t)x + gb[0], gj = (uint64_t)y + gb[1], gk = (uint64_t)z + gb[2];
+          real_t rr = 1.0 / (3.0) * (1.0 * gi / gstencil[0] + 1.0 * gj / gstencil[1] + 1.0 * gk / gstencil[2]);
+          uint64_t idx = 2 * ((((uint64_t)z * nny + y) * nnx + x) + n * f);
+          u[idx] = rr * 1.845703;
+          u[idx + 1] = rr * 1.845703 / 3.0;
+        }
+}
+
+/* the four orders in which the reference writes the staggered difference of two source fields */
+#define SD_A(P, Q, o) (P[i + (o)] - P[s + (o)] + Q[i + (o)] - Q[s + (o)])   /* cur - sub + cur - sub */
+#define SD_B(P, Q, o) (P[s + (o)] - P[i + (o)] + Q[s + (o)] - Q[i + (o)])   /* sub - cur + sub - cur */
+#define SD_C(P, Q, o) (P[s + (o)] + Q[s + (o)] - P[i + (o)] - Q[i + (o)])   /* sub + sub - cur - cur */
+#define SD_D(P, Q, o) (P[i + (o)] + Q[i + (o)] - P[s + (o)] - Q[s + (o)])   /* cur + cur - sub - sub */
+#define FLD(m) (u + (uint64_t)(m) * ln2)
+#define COE(m) (coef + (uint64_t)(m) * ln2)
+/* H component F (coefficients c = F, t = 6 + F), sources P, Q at offset OFF cells, difference SD */
+#define H_UPD(F, P, Q, OFF, SD, BND) do {                                                   \
+    real_t *h = FLD(F); const real_t *pp = FLD(P), *qq = FLD(Q);                             \
+    const real_t *cc = COE(F), *tt = COE(6 + (F));                                           \
+    const uint64_t s = i + 2 * (OFF);                                                        \
+    const real_t dR = SD(pp, qq, 0), dI = SD(pp, qq, 1);                                     \
+    real_t asgn;                                                                             \
+    if ((BND) >= 0) {                                                                        \
+      const real_t *bb = COE((BND) >= 0 ? (BND) : 0);                                        \
+      asgn     = h[i] * tt[i] - h[i + 1] * tt[i + 1] + bb[i] - cc[i] * dR + cc[i + 1] * dI;  \
+      h[i + 1] = h[i] * tt[i + 1] + h[i + 1] * tt[i] + bb[i + 1] - cc[i] * dI - cc[i + 1] * dR; \
+    } else {                                                                                 \
+      asgn     = h[i] * tt[i] - h[i + 1] * tt[i + 1] - cc[i] * dR + cc[i + 1] * dI;          \
+      h[i + 1] = h[i] * tt[i + 1] + h[i + 1] * tt[i] - cc[i] * dI - cc[i + 1] * dR;          \
+    }                                                                                        \
+    h[i] = asgn;                                                                             \
+  } while (0)
+/* E component F (6..11; coefficients c = 14 + F - 6, t = 20 + F - 6) */
+#define E_UPD(F, P, Q, OFF, SD, BND) do {                                                   \
+    real_t *e = FLD(F); const real_t *pp = FLD(P), *qq = FLD(Q);                             \
+    const real_t *cc = COE(14 + (F) - 6), *tt = COE(20 + (F) - 6);                           \
+    const uint64_t s = i + 2 * (OFF);                                                        \
+    const real_t dR = SD(pp, qq, 0), dI = SD(pp, qq, 1);                                     \
+    real_t asgn;                                                                             \
+    if ((BND) >= 0) {                                                                        \
+      const real_t *bb = COE((BND) >= 0 ? (BND) : 0);                                        \
+      asgn     = e[i] * tt[i] - e[i + 1] * tt[i + 1] + bb[i] + cc[i] * dR - cc[i + 1] * dI;  \
+      e[i + 1] = e[i] * tt[i + 1] + e[i + 1] * tt[i] + bb[i + 1] + cc[i] * dI + cc[i + 1] * dR; \
+    } else {                                                                                 \
+      asgn     = e[i] * tt[i] - e[i + 1] * tt[i + 1] + cc[i] * dR - cc[i + 1] * dI;          \
+      e[i + 1] = e[i] * tt[i + 1] + e[i + 1] * tt[i] + cc[i] * dI + cc[i + 1] * dR;          \
+    }                                                                                        \
+    e[i] = asgn;                                                                             \
+  } while (0)
+
+/* field numbers, src/kernels/solar_spt_blk.ic:29-41; coefficient numbers :44-60, :221-236 */
+enum { S_HYX = 0, S_HZX, S_HXY, S_HZY, S_HXZ, S_HYZ, S_EXZ, S_EYZ, S_EYX, S_EZX, S_EXY, S_EZY };
+enum { S_HXBND = 12, S_HYBND = 13, S_EXBND = 26, S_EYBND = 27 };
+
+/* which = 1: H update, 2: E update, 3: both (ALL_FIELDS), over the box [xb,xe) x [yb,ye) x [zb,ze) */
+void SFX(oracle_solar_step)(const int shape[3], int xb, int yb, int zb, int xe, int ye, int ze,
+                            const real_t *coef, real_t *u, int which)
+{
+  const int nnx = shape[0], nny = shape[1];
+  const uint64_t ln2 = 2 * (uint64_t)shape[0] * shape[1] * shape[2];
+  const int64_t SX = 1, SY = nnx, SZ = (int64_t)nnx * nny;
+  int x, j, k;
+  if (which & 1) {
+#pragma omp parallel for private(x, j) schedule(static)
+    for (k = zb; k < ze; k++)
+      for (j = yb; j < ye; j++)
+        for (x = xb; x < xe; x++) {
+          const uint64_t i = 2 * (((uint64_t)k * nny + j) * nnx + x);
+          H_UPD(S_HYX, S_EXY, S_EXZ, -SZ, SD_A, S_HYBND);   /* solar_spt_blk.ic:78-84 */
+          H_UPD(S_HZX, S_EXY, S_EXZ, -SY, SD_B, -1);        /* :100-106 */
+          H_UPD(S_HXY, S_EYX, S_EYZ, -SZ, SD_B, S_HXBND);   /* :122-128 */
+          H_UPD(S_HZY, S_EYX, S_EYZ, -SX, SD_A, -1);        /* :144-150 */
+          H_UPD(S_HXZ, S_EZX, S_EZY, -SY, SD_A, -1);        /* :166-172 */
+          H_UPD(S_HYZ, S_EZX, S_EZY, -SX, SD_C, -1);        /* :188-194 */
+        }
+  }
+  if (which & 2) {
+#pragma omp parallel for private(x, j) schedule(static)
+    for (k = zb; k < ze; k++)
+      for (j = yb; j < ye; j++)
+        for (x = xb; x < xe; x++) {
+          const uint64_t i = 2 * (((uint64_t)k * nny + j) * nnx + x);
+          E_UPD(S_EXZ, S_HZX, S_HZY, +SY, SD_B, -1);        /* solar_spt_blk.ic:263-269 */
+          E_UPD(S_EYZ, S_HZX, S_HZY, +SX, SD_D, -1);        /* :285-291 */
+          E_UPD(S_EYX, S_HXY, S_HXZ, +SZ, SD_B, S_EYBND);   /* :307-313 */
+          E_UPD(S_EZX, S_HXY, S_HXZ, +SY, SD_D, -1);        /* :329-335 */
+          E_UPD(S_EXY, S_HYX, S_HYZ, +SZ, SD_A, S_EXBND);   /* :351-357 */
+          E_UPD(S_EZY, S_HYX, S_HYZ, +SX, SD_B, -1);        /* :373-379 */
+        }
+  }
+}
+
+/* `nsteps` time steps on the undecomposed domain: what nb_naive_ts.c:187-203 does with U2 == 0
+ * (solar() falls back to the one array it has, solar_spt_blk.ic:392) -- nt calls, nt rounded up to even
+ * by the caller like oracle_run_naive */
+void SFX(oracle_solar_run)(const int shape[3], int nx, int nsteps, const real_t *coef, real_t *u)
+{
+  int s;
+  for (s = 0; s < nsteps; s++)
+    SFX(oracle_solar_step)(shape, 1, 1, 1, nx + 1, shape[1] - 1, shape[2] - 1, coef, u, 3);
 }

@@ -115,6 +115,16 @@ def make_problem(kernel, stencil, dtype=np.float64, alignment=8, padding=True,
     info = kernel_info(kernel)
     dtype = np.dtype(dtype)
     gstencil = tuple(stencil) if gstencil is None else tuple(gstencil)
+    if kernel == 6:
+        # solar: no array padding (src/utils.c:359-361), ONE array of 12 complex fields [f][z][y][x][re,im], U2 = 0
+        # (src/utils.c:168-172), 28 complex coefficient arrays (:199-201)
+        shape = domain_shape(stencil, info.r, alignment, False)
+        n = shape[0] * shape[1] * shape[2]
+        U1 = np.empty((12, shape[2], shape[1], shape[0], 2), dtype)
+        coef = np.zeros(n * 56, dtype)
+        getattr(lib(), "oracle_solar_init_coeff_" + _sfx(dtype))(C.c_uint64(n), _p(coef))
+        getattr(lib(), "oracle_solar_fill_" + _sfx(dtype))(_i3(shape), _i3(gstencil), _i3(gb), _p(U1))
+        return Problem(kernel, dtype, tuple(stencil), shape, info.r, U1, None, None, coef)
     shape = domain_shape(stencil, info.r, alignment, padding)
     n = shape[0] * shape[1] * shape[2]
     zyx = (shape[2], shape[1], shape[0])
@@ -142,12 +152,18 @@ def step(kernel, shape, box, coef, u, v, roc2, contract=False):
 
 def run_naive(pb: Problem, nt: int, contract=False) -> None:
     """The reference's ts 0 loop (nb_naive_ts.c:187-203): nt rounded up to even steps."""
+    if pb.kernel == 6:
+        return run_steps(pb, nt + (nt & 1), contract)
     getattr(lib(), "oracle_run_naive_" + _fsfx(pb.dtype, contract))(
         pb.kernel, _i3(pb.shape), pb.stencil[0], nt, _p(pb.coef), _p(pb.U1), _p(pb.U2), _p(pb.U3))
 
 
 def run_steps(pb: Problem, nsteps: int, contract=False) -> None:
     """Exactly nsteps steps, odd steps writing U1 (what ts 2 leaves: nsteps = nt-1)."""
+    if pb.kernel == 6:   # solar: every step updates the one array in place
+        getattr(lib(), "oracle_solar_run_" + _fsfx(pb.dtype, contract))(
+            _i3(pb.shape), pb.stencil[0], nsteps, _p(pb.coef), _p(pb.U1))
+        return
     getattr(lib(), "oracle_run_steps_" + _fsfx(pb.dtype, contract))(
         pb.kernel, _i3(pb.shape), pb.stencil[0], nsteps, _p(pb.coef), _p(pb.U1), _p(pb.U2), _p(pb.U3))
 
@@ -186,7 +202,10 @@ def ref_dump(kernel, stencil, nt, dtype=np.float64, ts=0, extra=(), threads=2, f
     hdr = np.frombuffer(raw[:32], np.int32)
     assert hdr[0] == 0x47495249 and hdr[1] == np.dtype(dtype).itemsize
     nnx, nny, nnz, r, nt_eff = (int(x) for x in hdr[2:7])
-    U1 = np.frombuffer(raw[32:], dtype).reshape(nnz, nny, nnx).copy()
+    if kernel == 6:   # solar: 12 complex fields in one array
+        U1 = np.frombuffer(raw[32:], dtype).reshape(12, nnz, nny, nnx, 2).copy()
+    else:
+        U1 = np.frombuffer(raw[32:], dtype).reshape(nnz, nny, nnx).copy()
     return U1, r, nt_eff
 
 

@@ -16,7 +16,8 @@
  * Usage: GIRIH_REF_DUMP=<file> ref_dump_{sp,dp} <mwd_kernel flags>
  * File layout: 8 x int32 header {magic 0x47495249, sizeof(real_t), nnx, nny, nnz,
  *              r, nt (after the diamond stepper's rounding), target_kernel}
- *              followed by nnx*nny*nnz real_t values of U1 (x fastest).
+ *              followed by nnx*nny*nnz real_t values of U1 (x fastest); for the solar slot
+ *              (table index 6, one array of 12 complex fields, src/utils.c:168-172) 24 times as many.
  */
 #include "driver.h"
 #include <stdint.h>
@@ -58,7 +59,7 @@ int main(int argc, char **argv)
   hdr[2] = p.ldomain_shape[0]; hdr[3] = p.ldomain_shape[1]; hdr[4] = p.ldomain_shape[2];
   hdr[5] = p.stencil.r; hdr[6] = p.nt; hdr[7] = p.target_kernel;
   fwrite(hdr, sizeof(int32_t), 8, fp);
-  fwrite(p.U1, sizeof(real_t), p.ln_domain, fp);
+  fwrite(p.U1, sizeof(real_t), p.stencil.type == SOLAR ? p.ln_domain * 24lu : p.ln_domain, fp);
   fclose(fp);
   MPI_Finalize();
   return 0;

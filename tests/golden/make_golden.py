@@ -18,6 +18,8 @@ the sizes BASELINE.json's configs name (C1 256^3 x 100 with both steppers, C2 51
 itself, C3 768^3 x 200 25-point, C4 512^3 x 200 per-point coefficients), fp64, so that the GPU parity suite compares
 the full-size runs with the reference and not with itself.  Takes several minutes of CPU time.
 
+`python tests/golden/make_golden.py solar` writes solar.json / solar_small.npz: outputs of the reference's solar kernel
+(table slot 6) through its ts 0 / ts 1 steppers.
 `python tests/golden/make_golden.py fma` writes small_fma.npz / checksums_fma.json instead: the same
 cases run by the reference built with FMA contraction (oracle/_ref/ref_dump_*_fast, gcc -O3 -mfma
 -ffp-contract=fast) -- the fixtures for the library's "contract" option.
@@ -83,6 +85,31 @@ def main_baseline():
             json.dump(sums, f, indent=1, sort_keys=True)
 
 
+# the solar slot (table index 6): (stencil, nt, ts); the reference needs an explicit --thread-group-size for ts 0 / 1
+# (its default -1 reaches `omp parallel num_threads(-1)`, src/kernels/solar_spt_blk.ic:65-66)
+SOLAR = [((24, 20, 18), 6, 0), ((17, 9, 11), 3, 0), ((40, 33, 29), 8, 1), ((64, 48, 40), 12, 0), ((130, 5, 40), 2, 0)]
+SOLAR_SMALL = ((9, 7, 6), 2, 0)
+
+
+def main_solar():
+    """solar.json: sha256 over the reference's whole array (12 fields x [z][y][x] x (re, im), frame included) after the run;
+    solar_small.npz: one tiny case in full."""
+    assert O.have_ref(), "build the reference first: make -C oracle ref"
+    sums, small = {}, {}
+    for dt, name in ((np.float32, "sp"), (np.float64, "dp")):
+        for st, nt, ts in SOLAR:
+            U1, r, nte = O.ref_dump(6, st, nt, dt, ts, threads=2)
+            sums[key(6, st, nt, ts, 0, name)] = {"sha256": hashlib.sha256(U1.tobytes()).hexdigest(),
+                                                 "max_abs": float(np.abs(U1).max())}
+        st, nt, ts = SOLAR_SMALL
+        U1, r, nte = O.ref_dump(6, st, nt, dt, ts, threads=2)
+        small[key(6, st, nt, ts, 0, name)] = U1
+    with open(os.path.join(HERE, "solar.json"), "w") as f:
+        json.dump(sums, f, indent=1, sort_keys=True)
+    np.savez_compressed(os.path.join(HERE, "solar_small.npz"), **small)
+    print(len(sums), "solar checksums,", len(small), "small cases")
+
+
 def ts_extra(ts, t_dim):
     return ("--t-dim", t_dim, "--thread-group-size", 1, "--num-wavefronts", 1) if ts == 2 else ()
 
@@ -117,7 +144,9 @@ def main(fast=False):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "baseline":
+    if len(sys.argv) > 1 and sys.argv[1] == "solar":
+        main_solar()
+    elif len(sys.argv) > 1 and sys.argv[1] == "baseline":
         main_baseline()
     else:
         main(fast=(len(sys.argv) > 1 and sys.argv[1] == "fma"))

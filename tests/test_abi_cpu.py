@@ -37,9 +37,9 @@ def test_kernel_table_matches_reference_list():
     for k, w in enumerate(want):
         d = G.kernel_info(k)
         assert (d.name, d.r, d.time_order, d.nd, d.coeff) == w
-    assert not G.kernel_info(6).gpu_supported
-    # algorithmic words per LUP, SURVEY.md 8(d)
-    assert [G.kernel_info(k).words_per_lup for k in (0, 1, 2, 3, 4, 5)] == [4, 2, 4, 6, 15, 9]
+    assert all(G.kernel_info(k).gpu_supported for k in range(8))   # the solar slot (6) has kernels since round 2
+    # algorithmic words per LUP; solar: 24 field reals in + out, 56 coefficient reals
+    assert [G.kernel_info(k).words_per_lup for k in (0, 1, 2, 3, 4, 5, 6)] == [4, 2, 4, 6, 15, 9, 104]
     assert [G.kernel_info(k).max_tfuse for k in (0, 1, 2, 3, 4, 5, 7)] == [1, 4, 3, 3, 1, 3, 1]
 
 
@@ -54,7 +54,8 @@ def test_argument_validation_and_no_cpu_fallback():
     assert _create(1, 2, (8, 8, 8), (16, 10, 10)) == 1
     assert _create(1, 8, (8, 8, 8), (16, 10, 11)) == 1            # nnz != nz + 2r
     assert _create(1, 8, (8, 8, 8), (16, 10, 10), 2, 2) == 1
-    assert _create(6, 8, (8, 8, 8), (16, 10, 10)) == 4            # solar: GIRIH_ERR_UNSUPPORTED
+    assert _create(6, 8, (8, 8, 8), (10, 10, 10), 0, 2) == 4      # solar on more than one rank: GIRIH_ERR_UNSUPPORTED
+    assert _create(6, 8, (8, 8, 8), (16, 10, 10)) == 1            # solar arrays are not padded (src/utils.c:359-361)
     if G.gpu_count() == 0:
         assert _create(1, 8, (8, 8, 8), (16, 10, 10)) == 2        # GIRIH_ERR_NO_DEVICE
         with pytest.raises(G.GirihError):
@@ -106,8 +107,8 @@ def test_cli_list_and_help_match_reference_behaviour(oracle):
     assert rc == 0 and "--target-kernel" in out
     rc, out, err = G.run_reference_cli(np.float32, ["--bogus-flag"])
     assert rc == 0 and "Invalid arguments" in err          # src/utils.c:1308-1323
-    rc, out, err = G.run_reference_cli(np.float32, ["--target-kernel", 6, "--verbose", 0])
-    assert rc == 1 and "unsupported configuration" in out  # src/kernels/stencils.h:40-47
+    rc, out, err = G.run_reference_cli(np.float32, ["--target-kernel", 6, "--target-ts", 2, "--verbose", 0])
+    assert rc == 1 and "unsupported configuration" in out  # solar + default wavefront: src/kernels/stencils.h:40-47
     rc, out, err = G.run_reference_cli(np.float32, ["--target-ts", 2, "--target-kernel", 0, "--mwd-type", 2,
                                                     "--nx", 32, "--ny", 32, "--nz", 32, "--t-dim", 1])
     assert rc == 1 and "Relaxed synchronization" in err     # diamond_utils.c:859

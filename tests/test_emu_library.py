@@ -86,6 +86,9 @@ test_autotune_then_results_are_unchanged = P.test_autotune_then_results_are_unch
 test_overlap_with_uneven_slabs_takes_one_schedule_on_every_rank = P.test_overlap_with_uneven_slabs_takes_one_schedule_on_every_rank
 test_pipelined_transfers_keep_jobs_apart = P.test_pipelined_transfers_keep_jobs_apart
 test_halo_push_matches_global_oracle = P.test_halo_push_matches_global_oracle
+test_solar_matches_the_reference = P.test_solar_matches_the_reference
+test_solar_schedules_chunks_and_boxes_match_oracle = P.test_solar_schedules_chunks_and_boxes_match_oracle
+test_solar_limits_are_reported = P.test_solar_limits_are_reported
 test_cli_verify = P.test_cli_verify
 test_cli_verify_contracted = P.test_cli_verify_contracted
 test_cli_autotune_prints_reference_prefix = P.test_cli_autotune_prints_reference_prefix

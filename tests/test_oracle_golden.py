@@ -103,3 +103,39 @@ def test_decomposed_fill_matches_global(oracle):
                                first=(1, 1, int(c == 0)), last=(1, 1, int(c == nparts - 1)))
             assert np.array_equal(s.U1, g.U1[gbz:gbz + lnz + 2 * r])
             assert np.array_equal(s.U3, g.U3[gbz:gbz + lnz + 2 * r])
+
+
+# ---- the solar slot (table index 6): tests/golden/solar.json / solar_small.npz, outputs of the reference's own solar
+# kernel through its ts 0 / ts 1 steppers (tests/golden/make_golden.py solar) --------------------------------------------
+SOLAR_SUMS = json.load(open(os.path.join(HERE, "golden", "solar.json")))
+SOLAR_SMALL = np.load(os.path.join(HERE, "golden", "solar_small.npz"))
+
+
+def _solar_key(name):
+    # k6_<nx>x<ny>x<nz>_nt<nt>_ts<ts>_td0_<sp|dp>
+    parts = name.split("_")
+    st = tuple(int(v) for v in parts[1].split("x"))
+    return st, int(parts[2][2:]), int(parts[3][2:]), (np.float32 if parts[5] == "sp" else np.float64)
+
+
+@pytest.mark.parametrize("name", sorted(SOLAR_SUMS))
+def test_solar_oracle_matches_reference_checksums(oracle, name):
+    import hashlib
+    st, nt, ts, dt = _solar_key(name)
+    pb = oracle.make_problem(6, st, dt)
+    oracle.run_naive(pb, nt)
+    assert hashlib.sha256(pb.U1.tobytes()).hexdigest() == SOLAR_SUMS[name]["sha256"]
+    assert float(np.abs(pb.U1).max()) == SOLAR_SUMS[name]["max_abs"]
+
+
+@pytest.mark.parametrize("name", sorted(SOLAR_SMALL.files))
+def test_solar_oracle_matches_reference_arrays(oracle, name):
+    st, nt, ts, dt = _solar_key(name)
+    pb = oracle.make_problem(6, st, dt)
+    assert pb.U1.shape == SOLAR_SMALL[name].shape == (12, st[2] + 2, st[1] + 2, st[0] + 2, 2)
+    before = pb.U1.copy()
+    oracle.run_naive(pb, nt)
+    assert pb.U1.tobytes() == SOLAR_SMALL[name].tobytes()
+    # the frame is never written, every interior value of every field moved
+    assert np.array_equal(pb.U1[:, 0], before[:, 0]) and np.array_equal(pb.U1[:, :, :, -1], before[:, :, :, -1])
+    assert not np.any(pb.U1[:, 1:-1, 1:-1, 1:-1] == before[:, 1:-1, 1:-1, 1:-1])

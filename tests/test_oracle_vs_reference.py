@@ -32,6 +32,17 @@ def test_ts2_dump(oracle, kernel, t_dim, st):
     assert U1.tobytes() == pb.U1.tobytes()
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("st,nt,ts", [((17, 11, 13), 5, 0), ((33, 6, 5), 4, 1), ((8, 70, 9), 2, 0)])
+def test_solar_dump(oracle, dt, st, nt, ts):
+    """table slot 6 through the reference's own solar kernel (src/kernels/solar_spt_blk.ic), whole array compared"""
+    _need_ref(oracle)
+    U1, r, nte = oracle.ref_dump(6, st, nt, dt, ts=ts)
+    pb = oracle.make_problem(6, st, dt)
+    oracle.run_naive(pb, nt)
+    assert U1.tobytes() == pb.U1.tobytes()
+
+
 def test_reference_own_verify_passes(oracle):
     """The reference binary built here satisfies its own bit-exact verifier."""
     _need_ref(oracle)
