@@ -45,7 +45,7 @@ enum girih_status {
   GIRIH_ERR_ARG = 1,          /* bad argument / shape                                   */
   GIRIH_ERR_NO_DEVICE = 2,    /* no CUDA device or driver: there is no CPU fallback     */
   GIRIH_ERR_CUDA = 3,         /* a CUDA runtime call failed (see girih_gpu_last_error)  */
-  GIRIH_ERR_UNSUPPORTED = 4,  /* table slot without a GPU operator (solar, kernel 6)    */
+  GIRIH_ERR_UNSUPPORTED = 4,  /* configuration the selected operator does not offer      */
   GIRIH_ERR_NCCL = 5,         /* NCCL missing or a NCCL call failed                     */
   GIRIH_ERR_STATE = 6,        /* call order (e.g. run before upload)                    */
   GIRIH_ERR_FRAME = 7         /* fused stepping needs identical Dirichlet frames in U1/U2 */
@@ -71,10 +71,24 @@ typedef struct {
   int n_coef_scalars;    /* scalar coefficients read from coef[] (constant kernels)     */
   int words_per_lup;     /* algorithmic words moved per lattice update      */
   int max_tfuse;         /* deepest temporal fusion the GPU stepper offers (>=1)        */
-  int gpu_supported;     /* 0 for the solar slot (src/kernels/stencils.h:40-47 analogue) */
+  int gpu_supported;     /* 1 for every slot since round 2 (0 = src/kernels/stencils.h:40-47 analogue) */
 } girih_kernel_desc;
 
-/* stencil_info_list[] of src/kernels/stencils.c:260-271: indices 0..7 as printed by --list. */
+/* stencil_info_list[] of src/kernels/stencils.c:260-271: indices 0..7 as printed by --list.
+ *
+ * Slot 6 ("solar", src/kernels/solar_spt_blk.ic:20-397) differs from the star / box operators in its data, exactly as in
+ * the reference: ONE field array of 12 complex components, u[12][nnz][nny][nnx][re,im] (src/utils.c:168-172; U2 == 0),
+ * and 28 complex coefficient arrays of the same shape (src/utils.c:199-201), no x padding (src/utils.c:359-361).
+ *   girih_gpu_create      domain_shape = stencil_shape + 2 in every direction; nranks must be 1 (the reference's halo
+ *                         exchange moves one real per cell, src/mpi_utils.c:173-200)
+ *   girih_gpu_upload      U1 = the field array (24 reals per cell), coef = the 56 reals per cell; U2 / U3 ignored (NULL)
+ *   girih_gpu_download    U1 only
+ *   girih_gpu_run_single  nsteps time steps; a time step is the H update of every interior cell followed by the E update
+ *                         (solar(), solar_spt_blk.ic:388-397, ALL_FIELDS), two kernel launches, in place
+ *   girih_gpu_step_box    solar() over a box of cells (dst ignored)
+ *   girih_gpu_run_fused, option contract, pipelined transfers: GIRIH_ERR_UNSUPPORTED (the reference's default wavefront
+ *                         table holds not_supported_mwd for this slot, src/kernels/stencils.c:303-311)
+ * words_per_lup = 104: 24 field reals read, 24 written, 56 coefficient reals read per cell and time step. */
 int girih_kernel_count(void);
 int girih_kernel_info(int target_kernel, girih_kernel_desc *out);
 
