@@ -92,9 +92,33 @@ def fuzz_library(seed, seconds, max_cases=10 ** 9, log=print):
     rnd = random.Random(seed)
     t0, n, bad = time.time(), 0, 0
     while time.time() - t0 < seconds and n < max_cases:
-        k = rnd.choice([0, 1, 1, 2, 3, 4, 5, 7])
+        k = rnd.choice([0, 1, 1, 2, 3, 4, 5, 6, 7])
         d = G.kernel_info(k)
         dt = rnd.choice([np.float32, np.float64])
+        if k == 6:   # solar slot: one rank, single steps; schedule variants, z chunks, repeated runs
+            gst = (rnd.randint(1, 140), rnd.randint(1, 20), rnd.randint(1, 40))
+            nsteps, tile, zchunk, reps = rnd.randint(1, 5), rnd.randint(0, 5), rnd.choice([0, 0, 1, 3, 7, 100]), rnd.choice([1, 2])
+            what = (k, np.dtype(dt).name, gst, nsteps, "tile", tile, "zchunk", zchunk, "reps", reps)
+            n += 1
+            try:
+                pb = G.make_problem(k, gst, dt)
+                s = EmuGpuStepper.for_problem(pb)
+                s.set_option("tile", tile)
+                s.set_option("zchunk", zchunk)
+                for _ in range(reps):
+                    s.run_single(nsteps, overlap=bool(rnd.getrandbits(1)))
+                s.download(pb.U1, None)
+                s.close()
+            except Exception as e:   # noqa: BLE001
+                bad += 1
+                log("ERROR", what, e)
+                continue
+            ob = O.make_problem(k, gst, dt)
+            O.run_steps(ob, nsteps * reps)
+            if pb.U1.tobytes() != ob.U1.tobytes():
+                bad += 1
+                log("MISMATCH", what)
+            continue
         xy = rnd.random() < 0.35
         dims = rnd.choice([(2, 1, 1), (1, 2, 1), (2, 2, 1), (1, 2, 2), (3, 1, 2), (2, 3, 1)]) if xy else \
             (1, 1, rnd.choice([1, 2, 3, 4, 5]))
