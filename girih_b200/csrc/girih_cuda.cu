@@ -1642,7 +1642,7 @@ extern "C" int girih_gpu_time_pass(girih_gpu_ctx *c, int tfuse, int reps, double
 static std::vector<int> tile_candidates(const girih_gpu_ctx *c, int T) {
   if (c->solar) return {1, 2, 3, 4, 5};
   if (c->opt_variant == 1) return {0};
-  if (c->kernel == 7) return {0, 4, 8, 116};
+  if (c->kernel == 7) return {0, 4, 8, 108, 116, 208, 216};
   if (c->kernel == 0) return {0, 8, 16, 108};
   if (c->kernel == 4) return {0, 8, 16};
   if (T == 1) {

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import girih_b200 as G  # noqa: E402
 
-cases = {4: [0, 8, 16], 7: [0, 4, 108, 116], 1: [0, 108, 208, 404, 408], 5: [0], 0: [0, 108]}
+cases = {4: [0, 8, 16], 7: [0, 116, 208, 216], 1: [0, 108, 208, 404, 408], 5: [0], 0: [0, 108]}
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 ks = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [4, 7, 1]
 for k in ks:
