@@ -324,11 +324,28 @@ def bench_configs(G, local, peak):
             steps = info["steps"]
             lups = float(n) ** 3 * steps * reps
             glups = lups / (ms * 1e-3) / 1e9
+            # the same run repeated until two in a row agree within 1% (at most 8 more): under the 1 000 W cap the power
+            # controller holds ~1 500 MHz for the first ~2 s of a heavy fp64 load and settles higher afterwards
+            # (profiles/r02_k0_sustained2.log), so the figure above can sit inside that transient
+            settled, prev, settle_runs = glups, None, 0
+            sampler2 = ClockSampler(local)
+            sampler2.start()
+            for _ in range(8):
+                s.run_ts(ts, nt, t_dim=td)
+                cur = float(n) ** 3 * steps / (s.elapsed_ms()["total"] * 1e-3) / 1e9
+                settle_runs += 1
+                done = prev is not None and abs(cur - prev) <= 0.01 * cur
+                prev = settled = cur
+                if done:
+                    break
+            clocks2 = sampler2.stop()
             T = info["tfuse"]
             ms_pass = s.time_pass(T, reps=10)
             alg = kd.words_per_lup * np.dtype(dt).itemsize * float(n) ** 3
             s.close()
-            out.append({"config": name, "glups": glups, "ms_per_run": ms / reps, "steps_executed": steps, "nt": nt_eff,
+            out.append({"config": name, "glups": glups, "glups_settled": settled, "settle_runs": settle_runs,
+                        "settled_sm_mhz": clocks2.get("sm_mhz"),
+                        "ms_per_run": ms / reps, "steps_executed": steps, "nt": nt_eff,
                         "fused_steps_per_pass": T, "ms_per_pass": ms_pass,
                         "pass_hbm_gbs": alg / (ms_pass * 1e-3) / 1e9, "pass_hbm_frac": alg / (ms_pass * 1e-3) / 1e9 / peak,
                         "single_step_roofline_glups": peak * 1e9 / (kd.words_per_lup * np.dtype(dt).itemsize) / 1e9,

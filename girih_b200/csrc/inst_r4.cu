@@ -94,10 +94,9 @@ static cudaError_t launch_r4_async_t(const StreamLaunch &s) {
 cudaError_t launch_r4(int kernel, int es, const StreamLaunch &s) {
   // tile option = warps (rows) per CTA
   // tile option: 8 / 16 = ring variant with that many rows per CTA, 108 / 116 = cp.async variant with 8 / 16 rows;
-  // default = cp.async variant with 16 rows per CTA.  Round 1 chose 8 rows on single-pass times at 512^3; sustained over
-  // 200 steps (what the BASELINE configs run, under the 1 000 W cap) 16 rows are faster at every size: fp64 168 / 179 /
-  // 161 against 154 / 154 / 151 GLUP/s at 512^3 / 768^3 / 1024^3, fp32 364 / 356 / 358 against 346 / 341 / 336
-  // (profiles/r02_k0_sustained.log).  The 2-rows-per-thread strip kernel of slot 4 was tried for slot 0: 114 / 234 GLUP/s.
+  // default = cp.async variant with 16 rows per CTA: 1-2% ahead of 8 rows once the power controller has settled under
+  // the 1 000 W cap (768^3: fp64 177.8 against 175.0 GLUP/s, fp32 347.5 against 344-346; profiles/r02_k0_sustained2.log).
+  // The 2-rows-per-thread strip kernel of slot 4 was tried for slot 0: 114 / 234 GLUP/s.
   if (s.contract) {   // contracted arithmetic: default kernels only
     if (kernel == 0) return es == 8 ? launch_r4_async_t<0, double, 16, true>(s) : launch_r4_async_t<0, float, 16, true>(s);
     if (kernel == 4) return es == 8 ? launch_r4_strip_t<4, double, 2, 8, true>(s) : launch_r4_strip_t<4, float, 2, 8, true>(s);
