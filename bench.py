@@ -324,17 +324,17 @@ def bench_configs(G, local, peak):
             steps = info["steps"]
             lups = float(n) ** 3 * steps * reps
             glups = lups / (ms * 1e-3) / 1e9
-            # the same run repeated until two in a row agree within 1% (at most 8 more): under the 1 000 W cap the power
-            # controller holds ~1 500 MHz for the first ~2 s of a heavy fp64 load and settles higher afterwards
-            # (profiles/r02_k0_sustained2.log), so the figure above can sit inside that transient
+            # the same run repeated at least 6 and at most 12 more times, until two in a row agree within 1%: under the
+            # 1 000 W cap the power controller holds ~1 500 MHz for the first 3-4 s of a heavy fp64 load and settles higher
+            # afterwards (profiles/r02_k0_sustained2.log), so the figure above can sit inside that transient
             settled, prev, settle_runs = glups, None, 0
             sampler2 = ClockSampler(local)
             sampler2.start()
-            for _ in range(8):
+            for _ in range(12):
                 s.run_ts(ts, nt, t_dim=td)
                 cur = float(n) ** 3 * steps / (s.elapsed_ms()["total"] * 1e-3) / 1e9
                 settle_runs += 1
-                done = prev is not None and abs(cur - prev) <= 0.01 * cur
+                done = settle_runs >= 6 and prev is not None and abs(cur - prev) <= 0.01 * cur
                 prev = settled = cur
                 if done:
                     break
