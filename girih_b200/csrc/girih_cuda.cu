@@ -1444,7 +1444,7 @@ static cudaError_t solar_step(girih_gpu_ctx *c, int xb, int yb, int zb, int xe, 
   s.nnx = c->hshape[0]; s.nny = c->hshape[1];
   s.xb = xb; s.xe = xe; s.yb = yb; s.ye = ye; s.zb = zb; s.ze = ze;
   s.zchunk = c->opt_zchunk;
-  s.tile = c->opt_tile;
+  s.tile = c->opt_tile ? c->opt_tile : c->tuned_tile[1];   // option, else what girih_gpu_autotune picked, else the default
   s.stream = c->s_comp;
   for (int ph = 0; ph < 2; ++ph) {
     if (!((phases >> ph) & 1)) continue;
