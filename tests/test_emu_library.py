@@ -205,3 +205,29 @@ def test_cli_halo_push(dt):
                                 "--t-dim", 3, "--verify", 1, "--npz", 3, "--gpu-push", 1, "--verbose", 0])
     assert rc == 0, out + err
     assert "eMax:0.000e+00|eL1:0.000e+00-PASSED" in out
+
+
+# ------------------------------------------------------------------------------------------------
+# bench.py's parity_check cases at the rank count of the driver's largest run: 8 z-slabs as 8 host threads, halos
+# moved by the halo-copy schedule.  With 8 ranks the slabs are 5-12 planes thin, i.e. the passes mix the copy schedule
+# and the blocking exchange (run_passes, girih_cuda.cu) -- the situation in which the emulator's fuzzer found a race.
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel,dt,gst,nsteps,tfuse", [(1, np.float64, (96, 64, 96), 18, 4), (1, np.float32, (70, 41, 41), 10, 3),
+                                                        (0, np.float32, (64, 40, 64), 8, 1), (5, np.float64, (70, 41, 48), 11, 3)])
+def test_bench_parity_cases_on_eight_ranks_with_halo_copy(kernel, dt, gst, nsteps, tfuse):
+    from oracle import girih_oracle as O
+
+    def fn(s):
+        if tfuse == 1:
+            s.run_single(nsteps, overlap=True)
+        else:
+            s.run_fused(nsteps, tfuse)
+
+    slabs = P._peer_linked_run(kernel, gst, dt, 8, fn, option="halo_copy")
+    ob = O.make_problem(kernel, gst, dt)
+    O.run_steps(ob, nsteps)
+    r = ob.r
+    for pb in slabs:
+        z0, lnz = pb.gb[2], pb.stencil[2]
+        assert np.array_equal(pb.U1[r:r + lnz], ob.U1[z0 + r:z0 + r + lnz])
+        assert np.array_equal(pb.U2[r:r + lnz], ob.U2[z0 + r:z0 + r + lnz])
